@@ -1,0 +1,236 @@
+/*
+ * partmanip_b200.h — C-ABI of the B200-native PartManip PPO hot path (libpartmanip_b200.so).
+ *
+ * The reference (PKU-EPIC/PartManip) has no FFI: its hot path is Python calling PyTorch.  This
+ * header is the seam the build introduces UNDER the reference's Python classes:
+ * every entry point replaces a span of reference Python/PyTorch code, cited as file:line relative
+ * to the reference root.  Conventions:
+ *   - plain C: raw DEVICE pointers, sizes, strides (in elements), a cudaStream_t passed as void*;
+ *     no torch types.  All tensors are fp32 row-major unless stated; "ld" = leading dimension
+ *     (row stride, elements).  Bool tensors are uint8 (torch.bool storage).
+ *   - every call is stream-ordered and asynchronous; none synchronises or allocates.  Workspaces
+ *     are caller-owned; their sizes come from the matching pm_*_ws_bytes() query.
+ *   - return value: PM_OK (0) or a negative pm_status.  pm_last_error() gives a message.
+ *   - device-side scalars (optimizer step, skip flag, counts) live in caller-owned device memory
+ *     so that whole minibatch steps can be captured in CUDA graphs without host round trips.
+ */
+#ifndef PARTMANIP_B200_H
+#define PARTMANIP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pm_stream_t; /* cudaStream_t */
+
+typedef enum {
+  PM_OK = 0,
+  PM_ERR_SHAPE = -1,
+  PM_ERR_ARG = -2,
+  PM_ERR_ALIGN = -3,
+  PM_ERR_CUDA = -4,
+  PM_ERR_UNSUPPORTED = -5
+} pm_status;
+
+/* algorithms/algo_utils/network.py:7-24 get_activation(); "crelu" maps to PM_ACT_RELU there. */
+typedef enum {
+  PM_ACT_NONE = 0,
+  PM_ACT_TANH = 1,
+  PM_ACT_RELU = 2,
+  PM_ACT_ELU = 3,
+  PM_ACT_SELU = 4,
+  PM_ACT_LRELU = 5,
+  PM_ACT_SIGMOID = 6
+} pm_act;
+
+/* arithmetic mode of the encoder's two GEMM layers */
+typedef enum {
+  PM_PREC_FP32 = 0, /* FFMA, fp32 everywhere: parity gate 1e-4 */
+  PM_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 accumulate in TMEM: parity gate 1e-2 */
+} pm_precision;
+
+const char* pm_last_error(void);
+int pm_version(void);
+/* 1 if the tcgen05 (sm_100a) encoder path was compiled in */
+int pm_has_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  running mean / std observation normaliser
+ * replaces algorithms/algo_utils/RMS.py:10-18 (RunningMeanStd.update) and :40-45
+ * (Normalization.__call__).  Split in four so a multi-GPU caller can all-reduce colsum / sqdev
+ * between the calls; pm_rms_forward chains them for one GPU.
+ * ------------------------------------------------------------------------------------------ */
+size_t pm_colreduce_ws_bytes(int rows, int cols);
+/* colsum[d] = sum_e x[e,d]                                   (x.mean(dim=0) numerator, RMS.py:14) */
+int pm_rms_colsum(const float* x, int64_t ldx, int E, int D, float* colsum, void* ws, pm_stream_t s);
+/* sqdev[d] = sum_e (x[e,d] - colsum[d]/count)^2               ((x-new_mean).pow(2).mean numerator, RMS.py:16)
+ * count = number of rows behind colsum (E, or the global env count when colsum was all-reduced) */
+int pm_rms_colsqdev(const float* x, int64_t ldx, int E, int D, const float* colsum, float count,
+                    float* sqdev, void* ws, pm_stream_t s);
+/* mean,S,std update with n = update counter AFTER the increment  (RMS.py:12-17) */
+int pm_rms_update(float* mean, float* S, float* std, const float* colsum, const float* sqdev,
+                  float count, int n, int D, pm_stream_t s);
+/* out = (x - mean) / std, no epsilon                            (RMS.py:44) */
+int pm_rms_normalize(const float* x, int64_t ldx, float* out, int64_t ldo, int E, int D,
+                     const float* mean, const float* std, pm_stream_t s);
+/* single-GPU chain; `scratch` holds 2*D floats + pm_colreduce_ws_bytes(E,D) */
+size_t pm_rms_forward_ws_bytes(int E, int D);
+int pm_rms_forward(const float* x, int64_t ldx, float* out, int64_t ldo, int E, int D, float* mean,
+                   float* S, float* std, int n_after, int update, void* scratch, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  GAE / returns / advantages
+ * replaces algorithms/algo_utils/storage.py:96-114 (RolloutStorage.compute_returns).
+ * rewards, values, returns, advantages: (T,E); dones, succs: (T,E) uint8; last_values: (E).
+ * use_succ_value=0 reproduces default_succ_value=None.  Bit-exact with the reference's op order.
+ * ------------------------------------------------------------------------------------------ */
+int pm_gae(const float* rewards, const float* values, const uint8_t* dones, const uint8_t* succs,
+           const float* last_values, float* returns, float* advantages, int T, int E, float gamma,
+           float gamma_lam, int use_succ_value, float succ_value, pm_stream_t s);
+/* x <- (x - mean(x)) / (std_unbiased(x) + 1e-8) over n elements  (storage.py:113-114, ppo.py:328-329) */
+size_t pm_normalize_ws_bytes(int64_t n);
+int pm_normalize_inplace(float* x, int64_t n, void* ws, pm_stream_t s);
+/* out <- normalised copy of x (mini_adv_norm works on the gathered minibatch copy) */
+int pm_normalize(const float* x, float* out, int64_t n, void* ws, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  Gaussian policy head and PPO losses
+ * ------------------------------------------------------------------------------------------ */
+/* standard-normal draws, Philox4x32-10 + Box-Muller; counter = (offset + element index) */
+int pm_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, pm_stream_t s);
+
+/* replaces actor_critic.py:36-47 (random_act_cri) after the actor forward:
+ *   raw = mu + exp(log_std)^2 * eps ; actions = tanh(raw)*max_action (squash=1) or raw (squash=0);
+ *   logp = MultivariateNormal(mu, scale_tril=diag(exp(log_std)^2)).log_prob(raw);
+ *   sigma = log_std broadcast to (E,A)  (SURVEY Q1, Q2).  actions/logp/sigma may be NULL. */
+int pm_policy_sample(const float* mu, const float* log_std, const float* eps, int E, int A,
+                     float max_action, int squash, float* actions, float* logp, float* sigma,
+                     pm_stream_t s);
+/* replaces actor_critic.py:58-65,84-91 (act / act_cri post-processing): out = tanh(mu)*max_action */
+int pm_action_activation(const float* mu, float* out, int64_t n, float max_action, int squash,
+                         pm_stream_t s);
+
+/* replaces actor_critic.py:71-82 (update_act_cri's distribution part, no gradient): log-prob of the stored
+ * squashed actions (Q4) and the Gaussian entropy.  logp / entropy: (B), either may be NULL. */
+int pm_policy_logprob(const float* mu, int64_t ldmu, const float* log_std, const float* actions, int B, int A,
+                      float max_action, int squash, float* logp, float* entropy, pm_stream_t s);
+
+/* replaces actor_critic.py:71-82 (log-prob of stored squashed actions, Q4) + ppo.py:326-344:
+ *   raw   = atanh(clamp(actions/max_action, +-(1-1e-5)))             (actor_critic.py:93-95)
+ *   logp  = log N(raw; mu, exp(2 log_std))
+ *   kl    = sum_a(ls - ls_old + (exp(ls_old)^2 + (mu_old-mu)^2)/(2 exp(ls)^2) - 0.5)   (ppo.py:332-333)
+ *   loss  = mean_b max(-adv*r, -adv*clamp(r,1-eps,1+eps)), r = exp(logp - logp_old)    (ppo.py:341-344)
+ * writes stats[0] = sum_b surrogate_b, stats[1] = sum_b kl_b (LOCAL sums; caller all-reduces),
+ * dmu[B,A] and dlog_std[A] = d(loss)/d(.) with the mean taken over 1/inv_batch samples.
+ * adv_stats: NULL, or device {mean, std+1e-8} (from pm_normalize) applied on the fly (mini_adv_norm). */
+size_t pm_ppo_actor_loss_ws_bytes(int B, int A);
+int pm_ppo_actor_loss(const float* mu, int64_t ldmu, const float* log_std, const float* actions,
+                      const float* logp_old, const float* mu_old, const float* sigma_old,
+                      const float* adv, const float* adv_stats, int B, int A, float inv_batch,
+                      float eps_clip, float max_action, int squash, float* stats, float* dmu,
+                      int64_t lddmu, float* dlog_std, float* logp_out, void* ws, pm_stream_t s);
+
+/* device-side replacement of ppo.py:334-338,355-357 bookkeeping (the host `continue`):
+ *   kl_mean = stats[1]*inv_batch; acc[3] = max(acc[3], kl_mean); skip = kl_mean > desired_kl;
+ *   if !skip: acc[0] += stats[0]*inv_batch; acc[1] += kl_mean; acc[2] += 1.
+ * skip_flag (int32) gates pm_adam_step. */
+int pm_ppo_actor_finalize(const float* stats, float inv_batch, float desired_kl, float* acc,
+                          int32_t* skip_flag, pm_stream_t s);
+
+/* replaces ppo.py:368-374: value loss (plain or clipped) forward + d/dv.  stats[0] += nothing;
+ * writes stats[0] = sum_b (v-target)^2 (LOCAL).  clip_delta: device scalar = mean|eps*old_v|
+ * (from pm_abs_mean) when clipped, else NULL. */
+int pm_value_loss(const float* v, int64_t ldv, const float* returns, const float* old_values,
+                  const float* clip_delta, int B, float inv_batch, float* stats, float* dv,
+                  int64_t lddv, void* ws, pm_stream_t s);
+/* replaces dagger.py:312-319 loss + backward to the student mean: stats[0] = mean((tea_act - act(mu))^2) over
+ * 1/inv_count elements (LOCAL sum * inv_count), dmu = d(loss)/d(mu).  tea_act: (B,A) contiguous. */
+int pm_dagger_loss(const float* mu, int64_t ldmu, const float* tea_act, int B, int A, float max_action, int squash,
+                   float inv_count, float* stats, float* dmu, int64_t lddmu, void* ws, pm_stream_t s);
+/* out[0] = scale * sum|x| (deterministic); used for delta_value_clipped (ppo.py:370) */
+int pm_abs_sum(const float* x, int64_t n, float scale, float* out, void* ws, pm_stream_t s);
+/* acc[idx] += stats[0]*scale  (mean_value_loss accumulation, ppo.py:384) */
+int pm_accumulate(const float* stats, float scale, float* acc, int idx, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  dense layers (MLP network.py:27-54; PointNet head network.py:152-159), fp32
+ * ------------------------------------------------------------------------------------------ */
+/* y[M,N] = act(x[M,K] W[N,K]^T + b[N]).  m_dev: NULL or device int32 row count (<= M). */
+int pm_linear_forward(const float* x, int64_t ldx, const float* W, const float* b, float* y,
+                      int64_t ldy, int M, int N, int K, int act, const int32_t* m_dev, pm_stream_t s);
+/* backward of one layer given dpre[M,N] = dL/d(pre-activation of this layer):
+ *   dW[N,K] = dpre^T x ; db[N] = colsum(dpre) ;
+ *   dx[M,K] = (dpre W) * act'(x) where x is the PREVIOUS layer's activated output and
+ *   act_prev its activation (PM_ACT_NONE: plain dx).  dx may be NULL (first layer). */
+size_t pm_linear_backward_ws_bytes(int M, int N, int K);
+int pm_linear_backward(const float* x, int64_t ldx, const float* W, const float* dpre, int64_t lddpre,
+                       float* dW, float* db, float* dx, int64_t lddx, int M, int N, int K,
+                       int act_prev, const int32_t* m_dev, void* ws, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * K1/K2  PointNet encoder: per-point MLP C->128->256->512 + symmetric pooling
+ * replaces network.py:165-182 (forward up to the pooled feature) and its autograd backward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float *W1, *b1; /* (128,C),(128)   mlp.0 */
+  const float *W2, *b2; /* (256,128),(256) mlp.2 */
+  const float *W3, *b3; /* (512,256),(512) mlp.4 */
+} pm_encoder_params;
+typedef struct {
+  float *W1, *b1, *W2, *b2, *W3, *b3;
+} pm_encoder_grads;
+
+/* in-place xyz centring through the caller's tensor (network.py:172-173) */
+int pm_pointnet_center(float* x, int64_t ldx, int B, int N, int C, pm_stream_t s);
+
+/* feat[b, 0:512] = max_n h3[b,n,:]; if feat_mean: feat_mean[b, 0:512] = mean_n h3[b,n,:]
+ * (both with row stride ldf; the caller lays them out as cat(max, mean, proprio)).
+ * argmax[b,512] (int32, may be NULL) = first point index attaining the max (needed by backward).
+ * h2mean[b,256] (may be NULL) = mean_n h2[b,n,:] (needed by the mean-branch backward). */
+int pm_pointnet_encode_forward(const float* x, int64_t ldx, int B, int N, int C,
+                               const pm_encoder_params* p, int act, int precision, float* feat,
+                               float* feat_mean, int64_t ldf, int32_t* argmax, float* h2mean,
+                               void* ws, size_t ws_bytes, pm_stream_t s);
+size_t pm_pointnet_encode_forward_ws_bytes(int B, int N, int C, int precision);
+
+/* Backward through max-pool + per-point MLP.  The max-pool routes dfeat[b,c] to the single point
+ * argmax[b,c], so only the unique "critical" points of each cloud carry gradient: their
+ * activations are recomputed from the 4C-byte inputs and layers 3..1 are back-propagated over
+ * those rows only.  Identical to autograd's result.  dfeat_mean != NULL adds the
+ * dense mean-pool branch (max_mean=True).  Gradients are OVERWRITTEN. */
+size_t pm_pointnet_encode_backward_ws_bytes(int B, int N, int C, int with_mean);
+int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C,
+                                const pm_encoder_params* p, int act, const float* dfeat,
+                                const float* dfeat_mean, int64_t lddf, const int32_t* argmax,
+                                const float* h2mean, const pm_encoder_grads* g, void* ws,
+                                size_t ws_bytes, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  grad-norm clip + Adam on flat buffers
+ * replaces nn.utils.clip_grad_norm_ + torch.optim.Adam.step (ppo.py:351-353, 381-382).
+ * The flat buffer is [clipped params (n_clip) | unclipped tail (log_std, Q8)].
+ * opt_state (device, 8 floats): [0]=step (float, incremented here unless skipped), [1]=lr,
+ *   [2..7] scratch written by pm_adam_prepare: total_norm, clip_coef, step_size, 1/sqrt(bc2), skipped.
+ * ------------------------------------------------------------------------------------------ */
+size_t pm_adam_ws_bytes(int64_t n);
+int pm_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 int64_t n_clip, float max_norm /* <=0: no clipping */, float beta1, float beta2,
+                 float eps, float* opt_state, const int32_t* skip_flag, void* ws, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  rollout-buffer helpers (storage.py:43-56 is cudaMemcpyAsync; the random sampler needs gathers)
+ * ------------------------------------------------------------------------------------------ */
+/* out[i,:] = src[idx[i],:]   (x[list] gathers of ppo.py:317-324 for sampler=random) */
+int pm_gather_rows(const float* src, int64_t lds, const int64_t* idx, float* out, int64_t ldo,
+                   int64_t n_rows, int width, pm_stream_t s);
+/* dst[rows,width] <- src (strided 2-D copy; add_transitions / add_transitions_dagger) */
+int pm_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n_rows, int width,
+                 pm_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARTMANIP_B200_H */

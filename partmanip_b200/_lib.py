@@ -1,0 +1,92 @@
+"""ctypes binding of libpartmanip_b200.so (C-ABI declared in include/partmanip_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a symbol is absent the import
+fails loudly.  Build it with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C partmanip_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpartmanip_b200.so")
+
+P, I, L, F, U64, SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
+
+
+class EncoderParams(C.Structure):
+    """pm_encoder_params / pm_encoder_grads (six device pointers W1,b1,W2,b2,W3,b3)."""
+    _fields_ = [(n, P) for n in ("W1", "b1", "W2", "b2", "W3", "b3")]
+
+
+EP = C.POINTER(EncoderParams)
+
+# name -> (restype, argtypes) ; mirrors include/partmanip_b200.h one to one
+SIGNATURES = {
+    "pm_last_error": (C.c_char_p, []),
+    "pm_version": (I, []),
+    "pm_has_tcgen05": (I, []),
+    "pm_colreduce_ws_bytes": (SZ, [I, I]),
+    "pm_rms_colsum": (I, [P, L, I, I, P, P, P]),
+    "pm_rms_colsqdev": (I, [P, L, I, I, P, F, P, P, P]),
+    "pm_rms_update": (I, [P, P, P, P, P, F, I, I, P]),
+    "pm_rms_normalize": (I, [P, L, P, L, I, I, P, P, P]),
+    "pm_rms_forward_ws_bytes": (SZ, [I, I]),
+    "pm_rms_forward": (I, [P, L, P, L, I, I, P, P, P, I, I, P, P]),
+    "pm_gae": (I, [P, P, P, P, P, P, P, I, I, F, F, I, F, P]),
+    "pm_normalize_ws_bytes": (SZ, [L]),
+    "pm_normalize_inplace": (I, [P, L, P, P]),
+    "pm_normalize": (I, [P, P, L, P, P]),
+    "pm_randn": (I, [P, L, U64, U64, P]),
+    "pm_policy_sample": (I, [P, P, P, I, I, F, I, P, P, P, P]),
+    "pm_action_activation": (I, [P, P, L, F, I, P]),
+    "pm_policy_logprob": (I, [P, L, P, P, I, I, F, I, P, P, P]),
+    "pm_ppo_actor_loss_ws_bytes": (SZ, [I, I]),
+    "pm_ppo_actor_loss": (I, [P, L, P, P, P, P, P, P, P, I, I, F, F, F, I, P, P, L, P, P, P, P]),
+    "pm_ppo_actor_finalize": (I, [P, F, F, P, P, P]),
+    "pm_value_loss": (I, [P, L, P, P, P, I, F, P, P, L, P, P]),
+    "pm_dagger_loss": (I, [P, L, P, I, I, F, I, F, P, P, L, P, P]),
+    "pm_abs_sum": (I, [P, L, F, P, P, P]),
+    "pm_accumulate": (I, [P, F, P, I, P]),
+    "pm_linear_forward": (I, [P, L, P, P, P, L, I, I, I, I, P, P]),
+    "pm_linear_backward_ws_bytes": (SZ, [I, I, I]),
+    "pm_linear_backward": (I, [P, L, P, P, L, P, P, P, L, I, I, I, I, P, P, P]),
+    "pm_pointnet_center": (I, [P, L, I, I, I, P]),
+    "pm_pointnet_encode_forward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, P, SZ, P]),
+    "pm_pointnet_encode_forward_ws_bytes": (SZ, [I, I, I, I]),
+    "pm_pointnet_encode_backward_ws_bytes": (SZ, [I, I, I, I]),
+    "pm_pointnet_encode_backward": (I, [P, L, I, I, I, EP, I, P, P, L, P, P, EP, P, SZ, P]),
+    "pm_adam_ws_bytes": (SZ, [L]),
+    "pm_adam_step": (I, [P, P, P, P, L, L, F, F, F, F, P, P, P, P]),
+    "pm_gather_rows": (I, [P, L, P, P, L, L, I, P]),
+    "pm_copy_rows": (I, [P, L, P, L, L, I, P]),
+}
+
+PM_ACT = {None: 0, "none": 0, "tanh": 1, "relu": 2, "crelu": 2, "elu": 3, "selu": 4, "lrelu": 5, "sigmoid": 6}
+PM_PREC = {"fp32": 0, "bf16": 1}
+
+
+class PMError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. There is no CPU/PyTorch fallback — "
+            "run `python -c 'import __graft_entry__ as g; g.build()'` (or `make -C partmanip_b200/csrc`).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise PMError(f"{what or 'libpartmanip_b200'} failed (rc={rc}): {lib.pm_last_error().decode()}")

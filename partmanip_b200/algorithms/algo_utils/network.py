@@ -1,0 +1,235 @@
+"""Network plugins `MLP` and `PointNet` — same constructor signature, parameter names and init order as
+the reference (algorithms/algo_utils/network.py:27-54, 141-198) so checkpoints and seeds carry over, but
+forward/backward run in the CUDA kernels of libpartmanip_b200.so (K1/K2/K3) instead of nn.Linear chains.
+
+`module(x)` is autograd-compatible (a torch.autograd.Function around the kernels, used by DAgger-style
+callers); the PPO engine drives `module.runner` directly on flat parameter/gradient buffers.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+
+_ACT_NAMES = ("elu", "selu", "relu", "crelu", "lrelu", "tanh", "sigmoid")
+
+
+class _Act(nn.Module):
+    """Stateless placeholder keeping nn.Sequential indices identical to the reference (0,2,4: Linear; 1,3: act)."""
+
+    def __init__(self, name: str):
+        super().__init__()
+        self.name = name
+
+    def forward(self, x):  # pragma: no cover - the kernels apply the activation
+        raise RuntimeError("activation modules are placeholders; use the owning network's forward")
+
+
+def get_activation(act_name: str):
+    """network.py:7-24 — unknown names print and return None there; here they raise (a None module would
+    only fail later inside nn.Sequential)."""
+    if act_name not in _ACT_NAMES:
+        raise NotImplementedError(f"invalid activation function {act_name!r}")
+    return _Act(act_name)
+
+
+class _Runner:
+    """Per-network kernel sequencing with buffers cached per batch size."""
+
+    def __init__(self, net: "nn.Module"):
+        self.net = net
+        self._bufs: Dict[int, dict] = {}
+
+    def params(self) -> List[torch.Tensor]:
+        return [p for p in self.net.parameters()]
+
+
+class _MLPRunner(_Runner):
+    def _get(self, B: int, dev):
+        b = self._bufs.get(B)
+        if b is None or b["dev"] != dev:
+            dims = self.net.dims
+            b = {"dev": dev,
+                 "h": [torch.empty(B, d, device=dev) for d in dims[1:]],
+                 "d": [torch.empty(B, d, device=dev) for d in dims[1:-1]]}
+            self._bufs[B] = b
+        return b
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        net = self.net
+        B = x.shape[0]
+        buf = self._get(B, x.device)
+        h = x
+        L = len(net.linears)
+        for i, lin in enumerate(net.linears):
+            act = net.act_name if i != L - 1 else None
+            h = ops.linear_forward(h, lin.weight, lin.bias, act, out=buf["h"][i])
+        return h
+
+    def backward(self, x: torch.Tensor, dout: torch.Tensor, grads: List[torch.Tensor]):
+        """grads: [W0,b0,W1,b1,...] tensors to overwrite; uses activations saved by the last forward(x)."""
+        net = self.net
+        B = x.shape[0]
+        buf = self._get(B, x.device)
+        L = len(net.linears)
+        dpre = dout
+        for i in reversed(range(L)):
+            lin = net.linears[i]
+            inp = x if i == 0 else buf["h"][i - 1]
+            dx = None if i == 0 else buf["d"][i - 1]
+            ops.linear_backward(inp, lin.weight, dpre, grads[2 * i], grads[2 * i + 1], dx,
+                                net.act_name if i > 0 else None)
+            dpre = dx
+
+
+class MLP(nn.Module):
+    """network.py:27-54.  Linear(in,h0)-act-...-Linear(h_last,out); orthogonal init, gains sqrt2.. then 1 / 0.01."""
+
+    def __init__(self, input_dim, output_dim, net_cfg, proprio_shape=0):
+        super().__init__()
+        hidden_dim = net_cfg['hid_dim']
+        activation = get_activation(net_cfg['activation'])
+        layers = [nn.Linear(input_dim, hidden_dim[0]), activation]
+        for l in range(len(hidden_dim)):
+            if l == len(hidden_dim) - 1:
+                layers.append(nn.Linear(hidden_dim[l], output_dim))
+            else:
+                layers.append(nn.Linear(hidden_dim[l], hidden_dim[l + 1]))
+                layers.append(activation)
+        self.model = nn.Sequential(*layers)
+        init_weights = [math.sqrt(2)] * len(hidden_dim)
+        self.output_dim = output_dim
+        init_weights.append(1 if output_dim == 1 else 0.01)
+        for idx, module in enumerate(m for m in self.model if isinstance(m, nn.Linear)):
+            torch.nn.init.orthogonal_(module.weight, gain=init_weights[idx])
+        self.act_name = net_cfg['activation']
+        self.dims = [input_dim, *hidden_dim, output_dim]
+        self.runner = _MLPRunner(self)
+
+    @property
+    def linears(self):
+        return [m for m in self.model if isinstance(m, nn.Linear)]
+
+    def forward(self, x):
+        return _NetFunction.apply(self, x, *self.parameters())
+
+
+class _PointNetRunner(_Runner):
+    def _get(self, B: int, dev):
+        b = self._bufs.get(B)
+        if b is None or b["dev"] != dev:
+            net = self.net
+            F = net.feat_dim
+            b = {"dev": dev,
+                 "feat": torch.empty(B, F, device=dev),
+                 "argmax": torch.empty(B, 512, device=dev, dtype=torch.int32),
+                 "h2mean": torch.empty(B, 256, device=dev) if net.max_mean_concat else None,
+                 "h1": torch.empty(B, 128, device=dev), "h2": torch.empty(B, 32, device=dev),
+                 "out": torch.empty(B, net.output_dim, device=dev),
+                 "dh2": torch.empty(B, 32, device=dev), "dh1": torch.empty(B, 128, device=dev),
+                 "dfeat": torch.empty(B, F, device=dev)}
+            self._bufs[B] = b
+        return b
+
+    def enc_params(self):
+        m = self.net.mlp
+        return [m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        net = self.net
+        B = x.shape[0]
+        N, C, p = net.point_num, net.in_channels, net.proprio_shape
+        buf = self._get(B, x.device)
+        if net.substract_mean:
+            ops.pointnet_center_(x, N, C)                      # in place through the caller's tensor (Q3)
+        feat = buf["feat"]
+        fmean = feat[:, 512:1024] if net.max_mean_concat else None
+        prec = net.precision if not net.max_mean_concat else "fp32"
+        ops.pointnet_encode_forward(x, N, C, self.enc_params(), net.act_name, prec, feat[:, :512], fmean,
+                                    buf["argmax"], buf["h2mean"])
+        if p:
+            ops.copy_rows(x[:, N * C:N * C + p], feat[:, net.feat_dim - p:])
+        f = net.final_mlp
+        ops.linear_forward(feat, f[0].weight, f[0].bias, net.act_name, out=buf["h1"])
+        ops.linear_forward(buf["h1"], f[2].weight, f[2].bias, net.act_name, out=buf["h2"])
+        return ops.linear_forward(buf["h2"], f[4].weight, f[4].bias, None, out=buf["out"])
+
+    def backward(self, x: torch.Tensor, dout: torch.Tensor, grads: List[torch.Tensor]):
+        """grads in parameter order: mlp.{0,2,4}.{weight,bias}, final_mlp.{0,2,4}.{weight,bias}."""
+        net = self.net
+        B = x.shape[0]
+        N, C = net.point_num, net.in_channels
+        buf = self._get(B, x.device)
+        f = net.final_mlp
+        ops.linear_backward(buf["h2"], f[4].weight, dout, grads[10], grads[11], buf["dh2"], net.act_name)
+        ops.linear_backward(buf["h1"], f[2].weight, buf["dh2"], grads[8], grads[9], buf["dh1"], net.act_name)
+        ops.linear_backward(buf["feat"], f[0].weight, buf["dh1"], grads[6], grads[7], buf["dfeat"], None)
+        dfm = buf["dfeat"][:, 512:1024] if net.max_mean_concat else None
+        ops.pointnet_encode_backward(x, N, C, self.enc_params(), net.act_name, buf["dfeat"][:, :512], buf["argmax"],
+                                     grads[0:6], dfm, buf["h2mean"])
+
+
+class PointNet(nn.Module):
+    """network.py:141-198.  Per-point Linear(C,128)-act-Linear(128,256)-act-Linear(256,512), max (| mean) pool,
+    [cat proprio], head Linear(F,128)-act-Linear(128,32)-act-Linear(32,out).  PyTorch default Linear init.
+
+    Build extensions over the reference (which hard-codes point_num=1024, network.py:146): `net_cfg['point_num']`
+    (default 1024) and `net_cfg['precision']` in {"fp32","bf16"} (default "fp32")."""
+
+    def __init__(self, input_dim, output_dim, net_cfg, proprio_shape=0):
+        super().__init__()
+        self.activation = get_activation(net_cfg['activation'])
+        self.max_mean_concat = bool(net_cfg['max_mean'])
+        self.point_num = int(net_cfg.get('point_num', 1024))
+        # network.py:148 — channels per point = input_dim // point_num (the floor absorbs a proprio tail < point_num)
+        self.in_channels = input_dim // self.point_num
+        self.mlp = nn.Sequential(
+            nn.Linear(input_dim // self.point_num, 128), self.activation,
+            nn.Linear(128, 256), self.activation,
+            nn.Linear(256, 512),
+        )
+        self.final_mlp = nn.Sequential(
+            nn.Linear(512 * (1 + self.max_mean_concat) + proprio_shape, 128), self.activation,
+            nn.Linear(128, 32), self.activation,
+            nn.Linear(32, output_dim),
+        )
+        self.proprio_shape = proprio_shape
+        self.substract_mean = bool(net_cfg['sub_mean'])
+        self.act_name = net_cfg['activation']
+        self.output_dim = output_dim
+        self.precision = net_cfg.get('precision', 'fp32')
+        if self.precision not in ("fp32", "bf16"):
+            raise NotImplementedError(f"precision {self.precision!r}")
+        self.feat_dim = 512 * (1 + self.max_mean_concat) + proprio_shape
+        self.runner = _PointNetRunner(self)
+
+    def forward(self, x):
+        return _NetFunction.apply(self, x, *self.parameters())
+
+
+class _NetFunction(torch.autograd.Function):
+    """Autograd bridge: forward/backward through the kernels; gradients w.r.t. the parameters only
+    (the observation is an input — the reference never differentiates through it either)."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        if x.shape[0] == 0:
+            raise ValueError("empty batch")
+        if x.dim() != 2:
+            raise ValueError(f"expected (batch, obs_dim), got {tuple(x.shape)}")
+        out = net.runner.forward(x)
+        ctx.net = net
+        ctx.save_for_backward(x)
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        net = ctx.net
+        (x,) = ctx.saved_tensors
+        grads = [torch.empty_like(p) for p in net.parameters()]
+        net.runner.backward(x, dout.contiguous(), grads)
+        return (None, None, *grads)

@@ -1,0 +1,137 @@
+"""RolloutStorage — mirror of algorithms/algo_utils/storage.py:7-138.
+
+Same attributes and methods; GAE runs in the K5 kernel, the sequential sampler yields contiguous
+ranges (a slice of the flattened (T*E, .) buffers, no gather) and the random sampler yields
+device index tensors consumed by pm_gather_rows.
+"""
+from __future__ import annotations
+
+import torch
+
+from ... import ops
+
+
+class _Range:
+    """A contiguous minibatch [start, stop) of the flattened buffer; iterable/len like the reference's index list."""
+    __slots__ = ("start", "stop")
+
+    def __init__(self, start, stop):
+        self.start, self.stop = start, stop
+
+    def __len__(self):
+        return self.stop - self.start
+
+    def __iter__(self):
+        return iter(range(self.start, self.stop))
+
+    def __getitem__(self, i):
+        return range(self.start, self.stop)[i]
+
+
+class RolloutStorage:
+
+    def __init__(self, num_envs, n_steps, obs_shape, actions_shape, device, default_succ_value=0, whole_adv_norm=False,
+                 sampler='sequential', tea_obs_shape=None, max_length=None):
+        self.device = device
+        self.sampler = sampler
+        self.n_steps = n_steps
+        self.num_envs = num_envs
+        self.step = 0
+        self.whole_adv_norm = whole_adv_norm
+        self.max_episode_length = max_length
+        self.first_fill = True
+        self.default_succ_value = default_succ_value
+        z = lambda *s, **k: torch.zeros(*s, device=self.device, **k)
+        if tea_obs_shape is not None:   # DAgger ring buffer (storage.py:20-27)
+            self.tea_obs = z(self.n_steps * self.num_envs, tea_obs_shape)
+            self.observations = z(self.n_steps * self.num_envs, obs_shape)
+            self.succ_flag = z(self.n_steps * self.num_envs, 1)
+            self.mix_buf_ind = 0
+            self.succ_buf_ind = (self.max_episode_length or 0) * self.num_envs
+            self.cur_buf_size = 0
+            self.last_episode_buf_ind = 0
+        else:                           # PPO (storage.py:28-41)
+            self.observations = z(self.n_steps, num_envs, obs_shape)
+            self.rewards = z(self.n_steps, num_envs, 1)
+            self.cur_buf_size = self.n_steps * self.num_envs
+            self.actions = z(self.n_steps, num_envs, actions_shape)
+            self.dones = z(self.n_steps, num_envs, 1).bool()
+            self.succs = z(self.n_steps, num_envs, 1).bool()
+            self.actions_log_prob = z(self.n_steps, num_envs, 1)
+            self.values = z(self.n_steps, num_envs, 1)
+            self.returns = z(self.n_steps, num_envs, 1)
+            self.advantages = z(self.n_steps, num_envs, 1)
+            self.mu = z(self.n_steps, num_envs, actions_shape)
+            self.sigma = z(self.n_steps, num_envs, actions_shape)
+            self.step_id = z(self.n_steps, num_envs, 1)
+
+    def obs_slot(self):
+        """The (E, D) view the next add_transitions will fill — producers may write into it directly."""
+        if self.step >= self.n_steps:
+            raise AssertionError("Rollout buffer overflow")
+        return self.observations[self.step]
+
+    def add_transitions(self, observations, actions, rewards, dones, succs, values, actions_log_prob, mu, sigma):
+        if self.step >= self.n_steps:
+            raise AssertionError("Rollout buffer overflow")
+        slot = self.observations[self.step]
+        if observations.data_ptr() != slot.data_ptr():          # already produced in place: nothing to move
+            ops.copy_rows(observations, slot)
+        self.actions[self.step].copy_(actions)
+        self.rewards[self.step].copy_(rewards.view(-1, 1))
+        self.dones[self.step].copy_(dones.view(-1, 1))
+        self.succs[self.step].copy_(succs.view(-1, 1))
+        self.values[self.step].copy_(values.view(-1, 1))
+        self.actions_log_prob[self.step].copy_(actions_log_prob.view(-1, 1))
+        self.mu[self.step].copy_(mu)
+        self.sigma[self.step].copy_(sigma)
+        self.step = self.step + 1
+
+    def add_transitions_dagger(self, stu_obs, tea_obs):
+        """storage.py:84-91."""
+        i = self.mix_buf_ind
+        ops.copy_rows(stu_obs, self.observations[i:i + self.num_envs])
+        ops.copy_rows(tea_obs, self.tea_obs[i:i + self.num_envs])
+        max_buf_size = self.n_steps * self.num_envs
+        self.mix_buf_ind = (self.mix_buf_ind + self.num_envs) % max_buf_size
+        if self.cur_buf_size < max_buf_size:
+            self.cur_buf_size += self.num_envs
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam):
+        """storage.py:96-114 in one K5 launch (+ one for whole_adv_norm)."""
+        sv = self.default_succ_value
+        ops.gae(self.rewards, self.values, self.dones, self.succs if sv is not None else None,
+                last_values.contiguous().view(-1), gamma, lam, sv, self.returns, self.advantages)
+        if self.whole_adv_norm:
+            ops.normalize_(self.advantages)
+
+    def mini_batch_generator(self, num_mini_batches):
+        """storage.py:125-138: size = min(buf // nmb, 2048), drop_last.  Returns a list (re-iterable like BatchSampler)."""
+        batch_size = self.cur_buf_size
+        mini_batch_size = min(int(batch_size // num_mini_batches), 2048)
+        if mini_batch_size <= 0:
+            return []
+        count = batch_size // mini_batch_size
+        if self.sampler == "sequential":
+            return [_Range(k * mini_batch_size, (k + 1) * mini_batch_size) for k in range(count)]
+        elif self.sampler == "random":
+            return _RandomBatches(batch_size, mini_batch_size, count, self.device)
+        raise NotImplementedError(self.sampler)
+
+
+class _RandomBatches:
+    """SubsetRandomSampler + BatchSampler(drop_last=True): a fresh permutation on every iteration."""
+
+    def __init__(self, n, size, count, device):
+        self.n, self.size, self.count, self.device = n, size, count, device
+
+    def __len__(self):
+        return self.count
+
+    def __iter__(self):
+        perm = torch.randperm(self.n, device=self.device)
+        for k in range(self.count):
+            yield perm[k * self.size:(k + 1) * self.size].contiguous()

@@ -1,0 +1,439 @@
+"""`ppo` — mirror of the reference PPO runner (algorithms/ppo.py:17-411): same constructor `(vec_env, cfg, logger)`,
+same `run / update / eval / save / resume` methods, same cfg keys, log keys and checkpoint format — with the
+whole learner (rollout-side network forwards, sampling, GAE, both update phases, grad-clip + Adam) executed by
+the CUDA kernels of libpartmanip_b200.so.
+
+What differs from the reference, on purpose (results unchanged):
+  * no host syncs inside the update: the KL-skip (`continue`, ppo.py:337-338) is a device predicate consumed by
+    the Adam kernel, loss / KL sums accumulate on the device and are read back once per iteration;
+  * each phase evaluates only the network it needs (the reference's update_act_cri runs both every time);
+  * sequential-sampler minibatches are slices of the rollout buffer (no gather);
+  * the per-env-step `print` with its four `.item()` syncs (ppo.py:229) is dropped.
+Multi-GPU: when torch.distributed is initialised every rank owns `num_envs` envs; gradients, the
+KL/loss sums and the observation statistics are all-reduced so all ranks take identical optimiser steps.
+"""
+from __future__ import annotations
+
+import os
+import time
+from copy import deepcopy
+from os.path import join as pjoin
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from .algo_utils import ActorCritic, Normalization, RolloutStorage
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class FlatAdam:
+    """torch.optim.Adam (defaults: betas (0.9, 0.999), eps 1e-8, no weight decay) over one flat buffer, stepped by
+    pm_adam_step.  state_dict()/load_state_dict() speak torch.optim's format so reference checkpoints round-trip
+    (ppo.py:89-90, 121-122)."""
+
+    def __init__(self, flat, params, offsets, group_sizes, lr, n_clip, max_norm):
+        self.flat, self.params, self.offsets, self.group_sizes = flat, params, offsets, group_sizes
+        self.grad = torch.zeros_like(flat)
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.opt_state = torch.zeros(8, device=flat.device, dtype=torch.float32)   # [0]=step [1]=lr (device scalars)
+        self.n_clip, self.max_norm = n_clip, max_norm
+        self.param_groups = [{'lr': lr} for _ in group_sizes]
+        self._lr_on_device = None
+        self.set_lr(lr)
+
+    def set_lr(self, lr):
+        for g in self.param_groups:
+            g['lr'] = lr
+        if self._lr_on_device != lr:
+            self.opt_state[1:2].fill_(float(lr))
+            self._lr_on_device = lr
+
+    def step(self, skip_flag=None):
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.n_clip, self.max_norm, self.opt_state,
+                      skip_flag)
+
+    @property
+    def step_count(self) -> int:
+        return int(self.opt_state[0].item())
+
+    def _views(self, flat):
+        return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
+
+    def state_dict(self):
+        step = self.opt_state[0].detach().cpu().clone()
+        state = {}
+        if float(step) > 0:
+            for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
+                state[i] = {'step': step.clone(), 'exp_avg': m.clone(), 'exp_avg_sq': v.clone()}
+        groups, k = [], 0
+        for g, n in zip(self.param_groups, self.group_sizes):
+            groups.append({'lr': g['lr'], 'betas': (0.9, 0.999), 'eps': 1e-08, 'weight_decay': 0, 'amsgrad': False,
+                           'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False,
+                           'fused': None, 'params': list(range(k, k + n))})
+            k += n
+        return {'state': state, 'param_groups': groups}
+
+    def load_state_dict(self, sd):
+        st = sd['state']
+        steps = []
+        for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
+            if i in st:
+                m.copy_(st[i]['exp_avg'])
+                v.copy_(st[i]['exp_avg_sq'])
+                steps.append(float(st[i]['step']))
+        # one step counter per flat buffer: the reference's two param groups always step together
+        self.opt_state[0:1].fill_(max(steps) if steps else 0.0)
+        self._lr_on_device = None
+        self.set_lr(sd['param_groups'][0]['lr'])
+
+
+class ppo:
+    def __init__(self, vec_env, cfg, logger):
+        # env infos (ppo.py:19-25)
+        self.vec_env = vec_env
+        self.num_envs = cfg['num_envs']
+        self.obs_mode = cfg['obs_mode']
+        self.num_obs = vec_env.num_obs[self.obs_mode]
+        self.num_actions = vec_env.num_actions
+        self.max_episode_length = vec_env.max_episode_length
+        self.default_succ_value = cfg['succ_value']
+        # training (ppo.py:27-33)
+        self.model_cfg = cfg['model']
+        self.max_iter = cfg['max_iterations']
+        self.n_steps = cfg['n_steps']
+        self.n_updates = cfg['n_updates']
+        self.num_mini_batches = cfg['n_minibatches']
+        self.device = cfg['device']
+        if not str(self.device).startswith('cuda'):
+            raise RuntimeError("partmanip_b200 runs on CUDA devices only (no CPU fallback); got device=%r" % (self.device,))
+        # eval and save (ppo.py:35-42)
+        self.eval_round = cfg['eval_round']
+        self.eval_freq = cfg['eval_frequence']
+        self.save_freq = cfg['save_frequence']
+        self.test_only = cfg['test_only']
+        self.save_pose = cfg['save_pose']
+        self.save_video = cfg['save_video']
+        self.save_ckpt_dir = logger.save_ckpt_dir
+        # learning rate (ppo.py:44-52)
+        self.lr_schedule = cfg['lr_schedule']
+        self.lr = cfg['lr']
+        self.desired_kl = cfg['desired_kl']
+        assert self.desired_kl > 0
+        if self.lr_schedule not in ('fixed', 'linear_decay', 'step_decay'):
+            raise NotImplementedError
+        # parameters (ppo.py:54-57)
+        self.epsilon_clip = cfg['epsilon_clip']
+        self.gamma = cfg['gamma']
+        self.lam = cfg['lam']
+        # tricks (ppo.py:59-68)
+        self.tricks = {}
+        self.tricks_keys = ['mini_adv_norm', 'whole_adv_norm', 'use_state_norm', 'use_clipped_value_loss', 'use_grad_clip']
+        for k in self.tricks_keys:
+            self.tricks[k] = cfg['tricks'][k]
+        self.max_grad_norm = cfg['tricks']['max_grad_norm'] if self.tricks['use_grad_clip'] else 0.0
+        if self.tricks['use_state_norm']:
+            self.state_norm = Normalization(shape=self.num_obs, device=self.device)
+            self.update_RMS = True
+        # network, buffer, optimisers (ppo.py:70-74)
+        self.world = _world()
+        self.actor_critic = ActorCritic(self.num_obs, self.num_actions, self.model_cfg).to(self.device)
+        ac = self.actor_critic.flatten_()
+        if self.world > 1:   # identical replicas
+            dist.broadcast(ac.actor_flat, 0)
+            dist.broadcast(ac.critic_flat, 0)
+        self.storage = RolloutStorage(self.num_envs, self.n_steps, self.num_obs, self.num_actions, self.device,
+                                      self.default_succ_value, self.tricks['whole_adv_norm'], cfg['sampler'])
+        a_params = list(ac.actor.parameters())
+        self.optimizer_actor = FlatAdam(ac.actor_flat, a_params + [ac.log_std], ac.actor_offs, [len(a_params), 1], self.lr,
+                                        ac.actor_n_clip, self.max_grad_norm)
+        c_params = list(ac.critic.parameters())
+        self.optimizer_critic = FlatAdam(ac.critic_flat, c_params, ac.critic_offs, [len(c_params)], self.lr,
+                                         ac.critic_flat.numel(), self.max_grad_norm)
+        self._actor_grads = ac.grad_views(self.optimizer_actor.grad, "actor")
+        self._critic_grads = ac.grad_views(self.optimizer_critic.grad, "critic")
+        # device-side bookkeeping for one update(): acc = [sum surrogate, sum kl, count, kl_max, sum value loss]
+        dev = self.device
+        self._acc = torch.zeros(8, device=dev)
+        self._stats_a = torch.zeros(2, device=dev)
+        self._stats_v = torch.zeros(2, device=dev)
+        self._skip = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._adv_stats = torch.zeros(2, device=dev)
+        self._clip_delta = torch.zeros(1, device=dev)
+        self._next_obs = torch.empty(self.num_envs, self.num_obs, device=dev)
+        self._mb = {}
+        # log
+        self.logger = logger
+        self.total_envsteps = 0
+        self.total_time = 0
+        self.curr_iter = 0
+        self.verbose = bool(cfg.get('verbose', False))
+        self.resume(cfg['resume'])
+
+    # ------------------------------------------------------------------ checkpoints (ppo.py:83-137)
+    def save(self, it):
+        os.makedirs(self.save_ckpt_dir, exist_ok=True)
+        save_path = pjoin(self.save_ckpt_dir, f'model_{it}.pth')
+        save_dict = {
+            'iteration': it,
+            'model_state_dict': {k: v.detach().clone() for k, v in self.actor_critic.state_dict().items()},
+            'optimizer_actor': self.optimizer_actor.state_dict(),
+            'optimizer_critic': self.optimizer_critic.state_dict(),
+            'total_steps': self.total_envsteps,
+            'tricks': self.tricks,
+            'obs_mode': self.obs_mode,
+            'model_cfg': self.model_cfg,
+        }
+        if self.tricks['use_state_norm']:
+            save_dict['state_running_ms'] = self.state_norm.running_ms.save()
+        torch.save(save_dict, save_path)
+        print(f'save ckpt to {save_path}!')
+
+    def resume(self, ckpt_path):
+        self.ckpt_path = ckpt_path
+        if ckpt_path is None:
+            return
+        print(f'load ckpt from {ckpt_path}!')
+        assert os.path.exists(ckpt_path)
+        ckpt_dict = torch.load(ckpt_path, map_location=self.device, weights_only=False)
+        self.actor_critic.load_state_dict(ckpt_dict["model_state_dict"])
+        self.optimizer_actor.load_state_dict(ckpt_dict["optimizer_actor"])
+        self.optimizer_critic.load_state_dict(ckpt_dict["optimizer_critic"])
+        self.curr_iter = ckpt_dict["iteration"]
+        self.total_envsteps = ckpt_dict["total_steps"]
+        for k in self.tricks_keys:
+            if self.tricks[k] != ckpt_dict['tricks'][k]:
+                print(f"WARNING: trick {k} is not consistent with ckpt! saved: {ckpt_dict['tricks'][k]}, now: {self.tricks[k]}")
+                if k == 'use_state_norm':
+                    print('this is not allowed')
+                    exit(1)
+        if self.tricks['use_state_norm']:
+            self.state_norm.running_ms.load(ckpt_dict['state_running_ms'])
+        assert self.obs_mode == ckpt_dict['obs_mode']
+
+    # ------------------------------------------------------------------ evaluation (ppo.py:139-203)
+    def eval(self):
+        self.actor_critic.eval()
+        self.vec_env.train_test_flag = 'test'
+        if self.test_only:
+            self.log_dict = {}
+        ep_infos = []
+        for r in range(self.eval_round):
+            curr_obs = self.vec_env.reset()[self.obs_mode]
+            for i in range(self.max_episode_length):
+                if self.tricks['use_state_norm']:
+                    curr_obs = self.state_norm(curr_obs, update=False)
+                actions, value = self.actor_critic.act_cri(curr_obs)
+                save_image_path = (pjoin(self.logger.save_video_dir, f"Iter{self.curr_iter}", f"{i}.png")
+                                   if self.save_video else None)
+                next_obs, rews, _, infos = self.vec_env.step(actions, save_image_path=save_image_path)
+                infos['action_t'] = actions[:, :3].mean(dim=-1)
+                infos['action_r'] = actions[:, 3:6].mean(dim=-1)
+                infos['action_gripper'] = actions[:, -1]
+                infos['succ_rate'] = self.vec_env.success
+                ep_infos.append(deepcopy(infos))
+                curr_obs = next_obs[self.obs_mode]
+        mode = 'Test' if self.test_only else 'Val'
+        self.use_info_update_logdict(ep_infos, mode)
+        if self.log_dict[f'{mode}/succ_rate_max'] > 0.5 and getattr(self, 'update_RMS', False):
+            self.update_RMS = False
+        ep_infos.clear()
+
+    # ------------------------------------------------------------------ rollout + learn (ppo.py:205-293)
+    def _ingest(self, env_obs, out):
+        """state-norm (or plain copy) of the env's observation into `out` (a rollout-buffer slot)."""
+        if self.tricks['use_state_norm']:
+            return self.state_norm(env_obs, update=self.update_RMS, out=out)
+        return ops.copy_rows(env_obs, out)
+
+    def collect(self, curr_obs, ep_infos=None, eps=None):
+        """ppo.py:225-248: n_steps of act -> env.step -> store; returns (obs after the last step, last_values)."""
+        st = self.storage
+        for t in range(self.n_steps):
+            actions, logp, values, mu, sigma = self.actor_critic.random_act_cri(curr_obs, None if eps is None else eps[t])
+            next_obs, rews, dones, infos = self.vec_env.step(actions)
+            if self.verbose:   # the reference prints every step (4 host syncs); opt-in here
+                print('TrainIter: %d, SuccRate: %.3f, Finish: %d, Rew: %.3f, maxRew: %.3f' % (
+                    self.curr_iter, infos['succ_rate'].data, dones.int().sum(), self.vec_env.rew_buf.mean(),
+                    self.vec_env.rew_buf.max()))
+            st.add_transitions(curr_obs, actions, rews, dones, self.vec_env.reset_succ, values, logp, mu, sigma)
+            if ep_infos is not None:
+                infos['action_t'] = actions[:, :3].abs().mean(dim=-1)
+                infos['action_r'] = actions[:, 3:6].abs().mean(dim=-1)
+                infos['action_gripper'] = actions[:, -1].abs()
+                infos['value_pred'] = values.squeeze(-1)
+                if self.tricks['use_state_norm']:
+                    ms = self.state_norm.running_ms
+                    infos['RMS_state_mean'] = ms.mean.mean().unsqueeze(0)
+                    infos['RMS_state_std'] = ms.std.mean().unsqueeze(0)
+                    infos['RMS_state_1_std'] = ms.std[:, :14].mean(dim=-1)
+                    infos['RMS_state_2_std'] = ms.std[:, 14:].mean(dim=-1)
+                ep_infos.append(deepcopy(infos))
+            out = st.obs_slot() if t + 1 < self.n_steps else self._next_obs
+            curr_obs = self._ingest(next_obs[self.obs_mode], out)
+        last_values = self.actor_critic.cri(curr_obs)
+        return curr_obs, last_values
+
+    def run(self):
+        if self.test_only:
+            self.eval()
+            self.logger.info(self.log_dict, self.curr_iter)
+            return
+        curr_obs = self._ingest(self.vec_env.reset()[self.obs_mode], self.storage.obs_slot())
+        while self.curr_iter < self.max_iter:
+            self.curr_iter += 1
+            self.actor_critic.train()
+            self.vec_env.train_test_flag = 'train'
+            self.log_dict = {}
+            ep_infos = []
+            start = time.time()
+            last_obs, last_values = self.collect(curr_obs, ep_infos)
+            torch.cuda.synchronize()
+            collection_time = time.time() - start
+
+            start = time.time()
+            self.storage.compute_returns(last_values, self.gamma, self.lam)
+            self.update(self.curr_iter)
+            self.storage.clear()
+            # the observation after the last step opens the next rollout: move it into slot 0
+            curr_obs = ops.copy_rows(last_obs, self.storage.obs_slot())
+            torch.cuda.synchronize()
+            learn_time = time.time() - start
+
+            self.total_envsteps += self.n_steps * self.vec_env.num_envs
+            self.total_time += collection_time + learn_time
+            action_std = self.actor_critic.log_std.detach().exp()
+            fps = int(self.n_steps * self.vec_env.num_envs / (collection_time + learn_time))
+            self.log_dict['Progress/total_steps'] = self.curr_iter
+            self.log_dict['Progress/collection_time'] = collection_time
+            self.log_dict['Progress/learn_time'] = learn_time
+            self.log_dict['Progress/FPS'] = fps
+            self.log_dict['Train/mean_action_noise_std'] = action_std.mean().item()
+            self.log_dict['Train/mean_t_noise_std'] = action_std[:3].mean()
+            self.log_dict['Train/mean_r_noise_std'] = action_std[3:-1].mean()
+            self.log_dict['Train/mean_gripper_noise_std'] = action_std[-1]
+            self.use_info_update_logdict(ep_infos, 'Train')
+
+            if self.curr_iter % self.eval_freq == 0:
+                self.eval()
+                self.storage.clear()
+                curr_obs = self._ingest(self.vec_env.reset()[self.obs_mode], self.storage.obs_slot())
+            if self.curr_iter % self.save_freq == 0:
+                self.save(self.curr_iter)
+            self.logger.info(self.log_dict, self.curr_iter)
+            ep_infos.clear()
+
+    def use_info_update_logdict(self, info_lst, mode):
+        """ppo.py:295-305 (logging only; plain torch)."""
+        if not info_lst:
+            return
+        for key in info_lst[0]:
+            assert len(info_lst[0][key].shape) == 1, f"{key}: {info_lst[0][key].shape}"
+            all_info = torch.stack([info[key].float() for info in info_lst], dim=-1)
+            self.log_dict[f'{mode}/{key}_mean'] = torch.mean(all_info)
+            self.log_dict[f'{mode}/{key}_max'] = torch.mean(all_info.max(dim=-1)[0])
+
+    # ------------------------------------------------------------------ the update (ppo.py:307-411)
+    def _minibatch(self, indices):
+        """Views (sequential sampler) or gathered copies (random sampler) of the eight per-sample tensors."""
+        st = self.storage
+        D, A = self.num_obs, self.num_actions
+        flat = dict(obs=st.observations.view(-1, D), act=st.actions.view(-1, A), val=st.values.view(-1, 1),
+                    ret=st.returns.view(-1, 1), logp=st.actions_log_prob.view(-1, 1), adv=st.advantages.view(-1, 1),
+                    mu=st.mu.view(-1, A), sigma=st.sigma.view(-1, A))
+        if hasattr(indices, 'start'):
+            return {k: v[indices.start:indices.stop] for k, v in flat.items()}
+        B = indices.numel()
+        out = self._mb.get(B)
+        if out is None:
+            out = {k: torch.empty(B, v.shape[1], device=v.device) for k, v in flat.items()}
+            self._mb[B] = out
+        for k, v in flat.items():
+            ops.gather_rows(v, indices, out[k])
+        return out
+
+    def update(self, it):
+        ac = self.actor_critic
+        world = self.world
+        self._acc.zero_()
+        batch = self.storage.mini_batch_generator(self.num_mini_batches)
+        squash = ac.action_activate == 'tanh'
+        dmu = dv = None
+        # ---- phase 1: actor (ppo.py:315-357)
+        for epoch in range(self.n_updates):
+            for indices in batch:
+                mb = self._minibatch(indices)
+                B = mb['obs'].shape[0]
+                inv_b = 1.0 / (B * world)
+                if dmu is None or dmu.shape[0] != B:
+                    dmu = torch.empty(B, self.num_actions, device=self.device)
+                    dv = torch.empty(B, 1, device=self.device)
+                mu = ac.actor.runner.forward(mb['obs'])
+                adv_stats = None
+                if self.tricks['mini_adv_norm']:
+                    adv_stats = ops.normalize_stats(mb['adv'].reshape(-1), self._adv_stats)
+                ops.ppo_actor_loss(mu, ac.log_std.data, mb['act'], mb['logp'].reshape(-1), mb['mu'], mb['sigma'],
+                                   mb['adv'].reshape(-1), adv_stats, inv_b, self.epsilon_clip, ac.max_action, squash,
+                                   self._stats_a, dmu, self._actor_grads[-1])
+                if world > 1:
+                    dist.all_reduce(self._stats_a)      # rank-consistent KL-skip decision
+                ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)
+                ac.actor.runner.backward(mb['obs'], dmu, self._actor_grads[:-1])
+                if world > 1:
+                    dist.all_reduce(self.optimizer_actor.grad)
+                self.optimizer_actor.step(self._skip)
+        # ---- phase 2: critic (ppo.py:359-384)
+        n_critic = 0
+        for epoch in range(self.n_updates):
+            for indices in batch:
+                mb = self._minibatch(indices)
+                B = mb['obs'].shape[0]
+                inv_b = 1.0 / (B * world)
+                if dv is None or dv.shape[0] != B:
+                    dv = torch.empty(B, 1, device=self.device)
+                v = ac.critic.runner.forward(mb['obs'])
+                clip_delta = None
+                if self.tricks['use_clipped_value_loss']:
+                    ops.abs_sum(mb['val'].reshape(-1), self.epsilon_clip * inv_b, self._clip_delta)
+                    if world > 1:
+                        dist.all_reduce(self._clip_delta)
+                    clip_delta = self._clip_delta
+                ops.value_loss(v, mb['ret'].reshape(-1), mb['val'].reshape(-1), clip_delta, inv_b, self._stats_v, dv)
+                ops.accumulate(self._stats_v, inv_b, self._acc, 4)
+                ac.critic.runner.backward(mb['obs'], dv, self._critic_grads)
+                if world > 1:
+                    dist.all_reduce(self.optimizer_critic.grad)
+                self.optimizer_critic.step(None)
+                n_critic += 1
+        # ---- one read-back per iteration
+        if world > 1:
+            dist.all_reduce(self._acc[4:5])
+        acc = self._acc.tolist()
+        count = int(round(acc[2]))
+        mean_value_loss = acc[4] / max(n_critic, 1)
+        if count == 0:
+            # the reference divides by count and raises ZeroDivisionError here (ppo.py:387); keep training instead
+            mean_surrogate_loss = mean_kl_mean = float('nan')
+        else:
+            mean_surrogate_loss = acc[0] / count
+            mean_kl_mean = acc[1] / count
+        # LR schedule touches the actor optimiser only (ppo.py:390-400)
+        if self.lr_schedule == 'linear_decay':
+            self.optimizer_actor.set_lr(max(self.lr * (1 - it / self.max_iter), 1e-5))
+        elif self.lr_schedule == 'step_decay':
+            self.optimizer_actor.set_lr(1e-5 if it > self.max_iter // 2 else self.lr)
+        if not hasattr(self, 'log_dict'):
+            self.log_dict = {}
+        self.log_dict['Train/value_gt_return_mean'] = self.storage.returns.mean()
+        self.log_dict['Train/value_gt_return_max'] = self.storage.returns.max()
+        self.log_dict['Train/learning_rate'] = self.optimizer_actor.param_groups[0]['lr']
+        self.log_dict['Train/value_function_loss'] = mean_value_loss
+        self.log_dict['Train/surrogate_loss'] = mean_surrogate_loss
+        self.log_dict['Train/kl'] = mean_kl_mean
+        self.log_dict['Train/kl_max'] = acc[3]
+        self.log_dict['Train/kl_update_count'] = count

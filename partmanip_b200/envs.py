@@ -1,0 +1,95 @@
+"""Synthetic zero-physics vec-env with the attribute/method surface the algo classes consume
+(reference tasks/hand_base.py:252-290, 363-402; SURVEY.md §1 'Env' row and §8(d) 'Synthetic inputs').
+
+It stands in for the closed Isaac Gym stepper in tests and in bench.py: observations come from a
+pre-generated pool cycled per step so RNG cost is excluded from timings.  `host=True` keeps the pool in
+pinned host memory and copies each step's observation host->device inside step()/reset() (the e2e
+measurement); otherwise the pool lives in HBM.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+
+class FakeVecEnv:
+    def __init__(self, num_envs: int, obs_dim: int, num_actions: int, device, *, obs_mode: str = "obs",
+                 cloud: bool = True, channels: int = 3, pool: int = 16, seed: int = 1234, succ_p: float = 0.0,
+                 done_p: float = 0.05, host: bool = False, extra_obs: Optional[Dict[str, int]] = None,
+                 max_episode_length: int = 200):
+        self.num_envs, self.num_actions, self.max_episode_length = num_envs, num_actions, max_episode_length
+        self.device = torch.device(device)
+        self.obs_mode = obs_mode
+        self.num_obs = {obs_mode: obs_dim, "proprio_state": 0}
+        self.extra = dict(extra_obs or {})
+        self.num_obs.update(self.extra)
+        self.train_test_flag = "train"
+        self.host = host
+        g = torch.Generator().manual_seed(seed)
+        E, D = num_envs, obs_dim
+
+        def make_obs():
+            if cloud:
+                # xyz ~ U over the open_drawer TSDF box x,y in (-1,1), z in (0.05,2.05) (cfg/tasks/open_drawer.yaml:12-14);
+                # 10 % of the points are exactly (0,0,0) like the env's invalid-point padding (utils/depth2tsdf.py:159)
+                n = D // channels
+                pc = torch.rand(E, n, channels, generator=g)
+                pc[..., :2] = pc[..., :2] * 2 - 1
+                pc[..., 2] = pc[..., 2] * 2 + 0.05
+                pc[torch.rand(E, n, generator=g) < 0.1] = 0.0
+                o = pc.reshape(E, n * channels)
+                if o.shape[1] < D:
+                    o = torch.cat([o, torch.randn(E, D - o.shape[1], generator=g)], dim=1)
+                return o
+            return torch.randn(E, D, generator=g)
+
+        self._pool = [make_obs() for _ in range(pool)]
+        self._extra_pool = {k: [torch.randn(E, d, generator=g) for _ in range(pool)] for k, d in self.extra.items()}
+        self._rew = [torch.randn(E, generator=g) for _ in range(pool)]
+        self._done = [torch.rand(E, generator=g) < done_p for _ in range(pool)]
+        self._succ = [torch.rand(E, generator=g) < succ_p for _ in range(pool)]
+        if host:
+            self._pool = [t.pin_memory() for t in self._pool]
+            self._obs_dev = torch.empty(E, D, device=self.device)
+            self._act_host = torch.empty(E, num_actions).pin_memory()
+        else:
+            self._pool = [t.to(self.device) for t in self._pool]
+        self._extra_pool = {k: [t.to(self.device) for t in v] for k, v in self._extra_pool.items()}
+        self._rew = [t.to(self.device) for t in self._rew]
+        self._done = [t.to(self.device) for t in self._done]
+        self._succ = [t.to(self.device) for t in self._succ]
+        self._k = 0
+        self.reset_succ = torch.zeros(E, dtype=torch.bool, device=self.device)
+        self.rew_buf = torch.zeros(E, device=self.device)
+        self.success = torch.zeros(1, device=self.device)
+        self.progress_buf = torch.zeros(E, dtype=torch.long, device=self.device)
+        self._zero = torch.zeros(1, device=self.device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _obs(self):
+        k = self._k % len(self._pool)
+        self._k += 1
+        if self.host:
+            self._obs_dev.copy_(self._pool[k], non_blocking=True)
+            self.h2d_bytes += self._pool[k].numel() * 4
+            o = self._obs_dev
+        else:
+            o = self._pool[k]
+        d = {self.obs_mode: o}
+        for name, v in self._extra_pool.items():
+            d[name] = v[k]
+        return d
+
+    def reset(self):
+        return self._obs()
+
+    def step(self, actions, save_image_path=None):
+        k = self._k % len(self._pool)
+        if self.host:   # the simulator consumes the actions on the host side of the boundary
+            self._act_host.copy_(actions, non_blocking=True)
+            self.d2h_bytes += actions.numel() * 4
+        self.rew_buf = self._rew[k]
+        self.reset_succ = self._succ[k]
+        return self._obs(), self.rew_buf, self._done[k], {"succ_rate": self._zero}

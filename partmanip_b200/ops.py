@@ -1,0 +1,344 @@
+"""Tensor-level wrappers over the C-ABI (include/partmanip_b200.h).
+
+Each function validates device/dtype/contiguity, passes raw device pointers + the current CUDA stream
+to libpartmanip_b200.so and returns torch tensors that merely OWN the memory (torch is plumbing here:
+allocation, streams, torch.distributed).  No function in this module computes anything with torch ops,
+and none falls back to CPU.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import EncoderParams, PM_ACT, PM_PREC, check, lib
+
+Tensor = torch.Tensor
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: Tensor, name: str, last_contig: bool = True) -> Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (the product path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if last_contig and t.dim() >= 1 and t.numel() > 0 and t.stride(-1) != 1:
+        raise ValueError(f"{name}: last dimension must be contiguous")
+    return t
+
+
+def _rows(t: Tensor, name: str) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a 2-D row-major view (row stride may exceed cols)."""
+    if t.dim() != 2:
+        raise ValueError(f"{name}: expected 2-D, got {tuple(t.shape)}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return t.shape[0], t.shape[1], ld
+
+
+_scratch = {}
+
+
+def scratch(nbytes: int, device, tag: str = "default") -> Tensor:
+    """Grow-only per-(device, tag) byte workspace (never shrinks, never shared across tags)."""
+    key = (str(device), tag)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------- K6 RMS
+def rms_forward(x: Tensor, out: Tensor, mean: Tensor, S: Tensor, std: Tensor, n_after: int, update: bool) -> Tensor:
+    """RMS.py:40-45 (+10-18 when update): out = (x-mean)/std after the optional running-stat update."""
+    _f32(x, "x"); _f32(out, "out")
+    E, D, ldx = _rows(x, "x")
+    _, _, ldo = _rows(out, "out")
+    for t, n in ((mean, "mean"), (S, "S"), (std, "std")):
+        _f32(t, n)
+        assert t.numel() == D and t.is_contiguous(), n
+    ws = scratch(lib.pm_rms_forward_ws_bytes(E, D), x.device, "rms")
+    check(lib.pm_rms_forward(_p(x), ldx, _p(out), ldo, E, D, _p(mean), _p(S), _p(std), int(n_after), int(bool(update)),
+                             _p(ws), _stream()), "pm_rms_forward")
+    return out
+
+
+def rms_colsum(x: Tensor, colsum: Tensor):
+    E, D, ldx = _rows(_f32(x, "x"), "x")
+    ws = scratch(lib.pm_colreduce_ws_bytes(E, D), x.device, "rms")
+    check(lib.pm_rms_colsum(_p(x), ldx, E, D, _p(_f32(colsum, "colsum")), _p(ws), _stream()), "pm_rms_colsum")
+
+
+def rms_colsqdev(x: Tensor, colsum: Tensor, count: float, sqdev: Tensor):
+    E, D, ldx = _rows(_f32(x, "x"), "x")
+    ws = scratch(lib.pm_colreduce_ws_bytes(E, D), x.device, "rms")
+    check(lib.pm_rms_colsqdev(_p(x), ldx, E, D, _p(colsum), float(count), _p(_f32(sqdev, "sqdev")), _p(ws), _stream()),
+          "pm_rms_colsqdev")
+
+
+def rms_update(mean: Tensor, S: Tensor, std: Tensor, colsum: Tensor, sqdev: Tensor, count: float, n_after: int):
+    check(lib.pm_rms_update(_p(mean), _p(S), _p(std), _p(colsum), _p(sqdev), float(count), int(n_after), mean.numel(),
+                            _stream()), "pm_rms_update")
+
+
+def rms_normalize(x: Tensor, out: Tensor, mean: Tensor, std: Tensor):
+    E, D, ldx = _rows(_f32(x, "x"), "x")
+    _, _, ldo = _rows(_f32(out, "out"), "out")
+    check(lib.pm_rms_normalize(_p(x), ldx, _p(out), ldo, E, D, _p(mean), _p(std), _stream()), "pm_rms_normalize")
+
+
+# ------------------------------------------------------------------------------------------- K5 GAE
+def gae(rewards: Tensor, values: Tensor, dones: Tensor, succs: Optional[Tensor], last_values: Tensor, gamma: float,
+        lam: float, succ_value: Optional[float], returns: Optional[Tensor] = None,
+        advantages: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """storage.py:96-112.  Shapes (T,E[,1]); dones/succs torch.bool or uint8."""
+    T, E = rewards.shape[0], rewards.shape[1]
+    for t, n in ((rewards, "rewards"), (values, "values"), (last_values, "last_values")):
+        _f32(t, n)
+        assert t.is_contiguous(), n
+    d8 = dones.view(torch.uint8) if dones.dtype == torch.bool else dones
+    s8 = None if succs is None else (succs.view(torch.uint8) if succs.dtype == torch.bool else succs)
+    assert d8.dtype == torch.uint8 and d8.is_contiguous()
+    if returns is None:
+        returns = torch.empty_like(rewards)
+    if advantages is None:
+        advantages = torch.empty_like(rewards)
+    use = succ_value is not None
+    # gamma*lam is a python double product rounded once to fp32, as `gamma * lam * advantage` evaluates it
+    check(lib.pm_gae(_p(rewards), _p(values), _p(d8), _p(s8), _p(last_values), _p(returns), _p(advantages), T, E,
+                     float(gamma), float(gamma * lam), int(use), float(succ_value if use else 0.0), _stream()), "pm_gae")
+    return returns, advantages
+
+
+def normalize_(x: Tensor) -> Tensor:
+    """(x-mean)/(std_unbiased+1e-8) in place (storage.py:113-114)."""
+    assert x.is_contiguous()
+    ws = scratch(256, x.device, "norm")
+    check(lib.pm_normalize_inplace(_p(_f32(x, "x")), x.numel(), _p(ws), _stream()), "pm_normalize_inplace")
+    return x
+
+
+def normalize_stats(x: Tensor, stats: Tensor) -> Tensor:
+    """stats <- {mean, std_unbiased+1e-8} of x without touching x (mini_adv_norm, ppo.py:328-329)."""
+    assert x.is_contiguous() and stats.numel() >= 2
+    check(lib.pm_normalize(_p(_f32(x, "x")), None, x.numel(), _p(_f32(stats, "stats")), _stream()), "pm_normalize")
+    return stats
+
+
+# ------------------------------------------------------------------------------------------- K4 policy
+def randn(out: Tensor, seed: int, offset: int) -> Tensor:
+    assert out.is_contiguous()
+    check(lib.pm_randn(_p(_f32(out, "out")), out.numel(), int(seed) & (2 ** 64 - 1), int(offset), _stream()), "pm_randn")
+    return out
+
+
+def policy_sample(mu: Tensor, log_std: Tensor, eps: Tensor, max_action: float, squash: bool,
+                  actions: Optional[Tensor] = None, logp: Optional[Tensor] = None, sigma: Optional[Tensor] = None):
+    """actor_critic.py:39-47 after the actor forward."""
+    E, A = mu.shape
+    for t, n in ((mu, "mu"), (log_std, "log_std"), (eps, "eps")):
+        _f32(t, n)
+        assert t.is_contiguous(), n
+    if actions is None:
+        actions = torch.empty_like(mu)
+    if logp is None:
+        logp = torch.empty(E, device=mu.device, dtype=torch.float32)
+    if sigma is None:
+        sigma = torch.empty_like(mu)
+    check(lib.pm_policy_sample(_p(mu), _p(log_std), _p(eps), E, A, float(max_action), int(bool(squash)), _p(actions),
+                               _p(logp), _p(sigma), _stream()), "pm_policy_sample")
+    return actions, logp, sigma
+
+
+def action_activation(mu: Tensor, max_action: float, squash: bool, out: Optional[Tensor] = None) -> Tensor:
+    assert mu.is_contiguous()
+    if out is None:
+        out = torch.empty_like(mu)
+    check(lib.pm_action_activation(_p(_f32(mu, "mu")), _p(out), mu.numel(), float(max_action), int(bool(squash)),
+                                   _stream()), "pm_action_activation")
+    return out
+
+
+def policy_logprob(mu: Tensor, log_std: Tensor, actions: Tensor, max_action: float, squash: bool):
+    """actor_critic.py:71-82 without gradient: (logp, entropy) of stored squashed actions."""
+    B, A, ldmu = _rows(_f32(mu, "mu"), "mu")
+    assert actions.is_contiguous()
+    logp = torch.empty(B, device=mu.device, dtype=torch.float32)
+    ent = torch.empty(B, device=mu.device, dtype=torch.float32)
+    check(lib.pm_policy_logprob(_p(mu), ldmu, _p(log_std), _p(_f32(actions, "actions")), B, A, float(max_action),
+                                int(bool(squash)), _p(logp), _p(ent), _stream()), "pm_policy_logprob")
+    return logp, ent
+
+
+def ppo_actor_loss(mu: Tensor, log_std: Tensor, actions: Tensor, logp_old: Tensor, mu_old: Tensor, sigma_old: Tensor,
+                   adv: Tensor, adv_stats: Optional[Tensor], inv_batch: float, eps_clip: float, max_action: float,
+                   squash: bool, stats: Tensor, dmu: Tensor, dlog_std: Tensor, logp_out: Optional[Tensor] = None):
+    """ppo.py:326-344 forward + analytic backward; see include/partmanip_b200.h."""
+    B, A, ldmu = _rows(_f32(mu, "mu"), "mu")
+    _, _, lddmu = _rows(_f32(dmu, "dmu"), "dmu")
+    for t, n in ((actions, "actions"), (logp_old, "logp_old"), (mu_old, "mu_old"), (sigma_old, "sigma_old"), (adv, "adv")):
+        _f32(t, n)
+        assert t.is_contiguous(), n
+    ws = scratch(lib.pm_ppo_actor_loss_ws_bytes(B, A), mu.device, "loss")
+    check(lib.pm_ppo_actor_loss(_p(mu), ldmu, _p(log_std), _p(actions), _p(logp_old), _p(mu_old), _p(sigma_old), _p(adv),
+                                _p(adv_stats), B, A, float(inv_batch), float(eps_clip), float(max_action),
+                                int(bool(squash)), _p(stats), _p(dmu), lddmu, _p(dlog_std), _p(logp_out), _p(ws),
+                                _stream()), "pm_ppo_actor_loss")
+
+
+def ppo_actor_finalize(stats: Tensor, inv_batch: float, desired_kl: float, acc: Tensor, skip_flag: Tensor):
+    assert skip_flag.dtype == torch.int32 and acc.numel() >= 4
+    check(lib.pm_ppo_actor_finalize(_p(stats), float(inv_batch), float(desired_kl), _p(acc), _p(skip_flag), _stream()),
+          "pm_ppo_actor_finalize")
+
+
+def value_loss(v: Tensor, returns: Tensor, old_values: Optional[Tensor], clip_delta: Optional[Tensor], inv_batch: float,
+               stats: Tensor, dv: Tensor):
+    """ppo.py:368-374 forward + d/dv.  v, dv: (B,1) or (B,) possibly strided."""
+    B = v.shape[0]
+    ldv = v.stride(0) if v.dim() > 1 or B > 1 else 1
+    lddv = dv.stride(0) if dv.dim() > 1 or B > 1 else 1
+    ws = scratch(4 * (B // 256 + 2) + 4096, v.device, "loss")
+    check(lib.pm_value_loss(_p(_f32(v, "v", False)), ldv, _p(returns), _p(old_values), _p(clip_delta), B,
+                            float(inv_batch), _p(stats), _p(_f32(dv, "dv", False)), lddv, _p(ws), _stream()),
+          "pm_value_loss")
+
+
+def dagger_loss(mu: Tensor, tea_act: Tensor, max_action: float, squash: bool, inv_count: float, stats: Tensor,
+                dmu: Tensor):
+    """dagger.py:312-314 forward + d/dmu."""
+    B, A, ldmu = _rows(_f32(mu, "mu"), "mu")
+    _, _, lddmu = _rows(_f32(dmu, "dmu"), "dmu")
+    assert tea_act.is_contiguous() and tea_act.shape == (B, A)
+    ws = scratch(4096, mu.device, "loss")
+    check(lib.pm_dagger_loss(_p(mu), ldmu, _p(_f32(tea_act, "tea_act")), B, A, float(max_action), int(bool(squash)),
+                             float(inv_count), _p(stats), _p(dmu), lddmu, _p(ws), _stream()), "pm_dagger_loss")
+
+
+def abs_sum(x: Tensor, scale: float, out: Tensor):
+    assert x.is_contiguous()
+    ws = scratch(4096, x.device, "loss")
+    check(lib.pm_abs_sum(_p(_f32(x, "x")), x.numel(), float(scale), _p(out), _p(ws), _stream()), "pm_abs_sum")
+
+
+def accumulate(stats: Tensor, scale: float, acc: Tensor, idx: int):
+    check(lib.pm_accumulate(_p(stats), float(scale), _p(acc), int(idx), _stream()), "pm_accumulate")
+
+
+# ------------------------------------------------------------------------------------------- K3 dense
+def linear_forward(x: Tensor, W: Tensor, b: Optional[Tensor], act, out: Optional[Tensor] = None,
+                   m_dev: Optional[Tensor] = None) -> Tensor:
+    M, K, ldx = _rows(_f32(x, "x"), "x")
+    N = W.shape[0]
+    assert W.shape[1] == K and W.is_contiguous() and _f32(W, "W") is W
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    _, _, ldy = _rows(out, "out")
+    check(lib.pm_linear_forward(_p(x), ldx, _p(W), _p(b), _p(out), ldy, M, N, K, PM_ACT[act], _p(m_dev), _stream()),
+          "pm_linear_forward")
+    return out
+
+
+def linear_backward(x: Tensor, W: Tensor, dpre: Tensor, dW: Tensor, db: Optional[Tensor], dx: Optional[Tensor],
+                    act_prev, m_dev: Optional[Tensor] = None):
+    M, K, ldx = _rows(_f32(x, "x"), "x")
+    N = W.shape[0]
+    _, _, ldd = _rows(_f32(dpre, "dpre"), "dpre")
+    lddx = 0
+    if dx is not None:
+        _, _, lddx = _rows(_f32(dx, "dx"), "dx")
+    ws = scratch(lib.pm_linear_backward_ws_bytes(M, N, K), x.device, "linbwd")
+    check(lib.pm_linear_backward(_p(x), ldx, _p(W), _p(dpre), ldd, _p(dW), _p(db), _p(dx), lddx, M, N, K,
+                                 PM_ACT[act_prev], _p(m_dev), _p(ws), _stream()), "pm_linear_backward")
+
+
+# ------------------------------------------------------------------------------------------- K1/K2 encoder
+def _enc_struct(ts: Sequence[Tensor]) -> EncoderParams:
+    assert len(ts) == 6
+    for t in ts:
+        _f32(t, "encoder tensor")
+        assert t.is_contiguous()
+    return EncoderParams(*[t.data_ptr() for t in ts])
+
+
+def pointnet_center_(x: Tensor, N: int, C: int):
+    """network.py:172-173 — in place through the caller's tensor (Q3).  x: (B, >= N*C)."""
+    B, _, ldx = _rows(_f32(x, "x"), "x")
+    check(lib.pm_pointnet_center(_p(x), ldx, B, N, C, _stream()), "pm_pointnet_center")
+
+
+def pointnet_encode_forward(x: Tensor, N: int, C: int, enc_params: Sequence[Tensor], act, precision: str, feat: Tensor,
+                            feat_mean: Optional[Tensor] = None, argmax: Optional[Tensor] = None,
+                            h2mean: Optional[Tensor] = None):
+    """network.py:175-182.  x: (B, >= N*C) rows; feat/feat_mean: (B, 512) views with a common row stride."""
+    B, width, ldx = _rows(_f32(x, "x"), "x")
+    assert width >= N * C
+    _, fw, ldf = _rows(_f32(feat, "feat"), "feat")
+    assert fw == 512
+    if feat_mean is not None:
+        assert _rows(feat_mean, "feat_mean")[2] == ldf
+    if argmax is not None:
+        assert argmax.dtype == torch.int32 and argmax.is_contiguous() and argmax.shape == (B, 512)
+    prec = PM_PREC[precision]
+    nbytes = lib.pm_pointnet_encode_forward_ws_bytes(B, N, C, prec)
+    ws = scratch(nbytes, x.device, "encfwd") if nbytes else None
+    ps = _enc_struct(enc_params)
+    check(lib.pm_pointnet_encode_forward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], prec,
+                                         _p(feat), _p(feat_mean), ldf, _p(argmax), _p(h2mean), _p(ws), nbytes, _stream()),
+          "pm_pointnet_encode_forward")
+
+
+def pointnet_encode_backward(x: Tensor, N: int, C: int, enc_params: Sequence[Tensor], act, dfeat: Tensor,
+                             argmax: Tensor, enc_grads: Sequence[Tensor], dfeat_mean: Optional[Tensor] = None,
+                             h2mean: Optional[Tensor] = None):
+    """autograd of network.py:175-182 w.r.t. the six encoder tensors (gradients overwritten)."""
+    B, width, ldx = _rows(_f32(x, "x"), "x")
+    _, fw, lddf = _rows(_f32(dfeat, "dfeat"), "dfeat")
+    assert fw == 512 and argmax.dtype == torch.int32 and argmax.is_contiguous()
+    nbytes = lib.pm_pointnet_encode_backward_ws_bytes(B, N, C, int(dfeat_mean is not None))
+    ws = scratch(nbytes, x.device, "encbwd")
+    ps, gs = _enc_struct(enc_params), _enc_struct(enc_grads)
+    check(lib.pm_pointnet_encode_backward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], _p(dfeat), _p(dfeat_mean), lddf,
+                                          _p(argmax), _p(h2mean), ct.byref(gs), _p(ws), nbytes, _stream()),
+          "pm_pointnet_encode_backward")
+
+
+# ------------------------------------------------------------------------------------------- K7 optimiser
+def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, n_clip: int, max_norm: float,
+              opt_state: Tensor, skip_flag: Optional[Tensor], beta1: float = 0.9, beta2: float = 0.999,
+              eps: float = 1e-8):
+    n = params.numel()
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        _f32(t, "adam buffer")
+        assert t.is_contiguous() and t.numel() == n
+    assert opt_state.numel() >= 8 and opt_state.dtype == torch.float32
+    ws = scratch(lib.pm_adam_ws_bytes(n), params.device, "adam")
+    check(lib.pm_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), n, int(n_clip), float(max_norm),
+                           float(beta1), float(beta2), float(eps), _p(opt_state), _p(skip_flag), _p(ws), _stream()),
+          "pm_adam_step")
+
+
+# ------------------------------------------------------------------------------------------- K8 storage
+def gather_rows(src: Tensor, idx: Tensor, out: Tensor) -> Tensor:
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and idx.is_cuda
+    _, w, lds = _rows(_f32(src, "src"), "src")
+    n, w2, ldo = _rows(_f32(out, "out"), "out")
+    assert w == w2 and n == idx.numel()
+    check(lib.pm_gather_rows(_p(src), lds, _p(idx), _p(out), ldo, n, w, _stream()), "pm_gather_rows")
+    return out
+
+
+def copy_rows(src: Tensor, dst: Tensor) -> Tensor:
+    n, w, lds = _rows(_f32(src, "src"), "src")
+    n2, w2, ldd = _rows(_f32(dst, "dst"), "dst")
+    assert (n, w) == (n2, w2)
+    check(lib.pm_copy_rows(_p(src), lds, _p(dst), ldd, n, w, _stream()), "pm_copy_rows")
+    return dst

@@ -1,0 +1,235 @@
+"""GPU parity tests for the PointNet encoder kernels (K1/K2) and for whole PPO iterations driven through the
+reference-shaped `ppo` class, against fixtures recorded from the unmodified reference (tests/golden) and the
+CPU oracle.  All kernels are reached through the C-ABI."""
+import math
+
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+from tests.helpers import ITER_CASES, close, load_golden, max_err, ppo_cfg, sub
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(t):
+    return t.to(DEV).contiguous()
+
+
+PN_CASES = {
+    "pointnet_base_a10.npz": dict(D=3072, out=10, proprio=0, cfg=dict(activation="tanh", max_mean=False, sub_mean=False)),
+    "pointnet_submean_proprio.npz": dict(D=3097, out=7, proprio=25, cfg=dict(activation="tanh", max_mean=False, sub_mean=True)),
+    "pointnet_relu_submean.npz": dict(D=3072, out=10, proprio=0, cfg=dict(activation="relu", max_mean=False, sub_mean=True)),
+    "pointnet_n2048_c3.npz": dict(D=6144, out=10, proprio=0, cfg=dict(activation="tanh", max_mean=False, sub_mean=False, point_num=2048)),
+    "pointnet_maxmean_c4.npz": dict(D=4096, out=10, proprio=0, cfg=dict(activation="tanh", max_mean=True, sub_mean=False)),
+}
+
+
+def _build(name, precision="fp32"):
+    from partmanip_b200.algorithms.algo_utils.network import PointNet
+    g = load_golden(name)
+    c = PN_CASES[name]
+    net = PointNet(c["D"], c["out"], dict(name="PointNet", precision=precision, **c["cfg"]), c["proprio"])
+    net.load_state_dict(sub(g, "w"))
+    return g, net.to(DEV)
+
+
+@pytest.mark.parametrize("name", list(PN_CASES))
+def test_pointnet_golden_forward(name):
+    g, net = _build(name)
+    assert sum(p.numel() for p in net.parameters()) == int(g["n_params"])
+    x = cu(g["x"])
+    with torch.no_grad():
+        y = net(x)
+    assert close(y.cpu(), g["y"], 1e-4, 1e-5), max_err(y.cpu(), g["y"])
+    # Q3: sub_mean centres the caller's tensor in place
+    assert close(x.cpu(), g["x_after"], 1e-5, 1e-6)
+    if PN_CASES[name]["cfg"]["sub_mean"]:
+        assert not torch.equal(x.cpu(), g["x"])
+
+
+@pytest.mark.parametrize("name", [n for n in PN_CASES if not PN_CASES[n]["cfg"]["max_mean"]])
+def test_pointnet_golden_backward(name):
+    g, net = _build(name)
+    y = net(cu(g["x"]))
+    y.square().sum().backward()
+    for k, v in sub(g, "g").items():
+        got = dict(net.named_parameters())[k].grad.cpu()
+        # gradient gate: 1e-4 relative to the tensor's scale (sums over 10^3..10^4 fp32 terms reorder freely)
+        tol = 1e-4 * float(v.abs().max()) + 1e-6
+        assert float((got - v).abs().max()) <= tol, (k, float((got - v).abs().max()), tol)
+
+
+def test_pointnet_argmax_first_index_and_duplicates():
+    """Ties between bit-identical points (the env's (0,0,0) padding) resolve to the first index, like torch.max."""
+    from partmanip_b200 import ops
+    torch.manual_seed(5)
+    B, N, C = 3, 1024, 3
+    x = torch.rand(B, N * C) * 2 - 1
+    x.view(B, N, C)[:, 100:400] = 0.0                      # 300 duplicate points per cloud
+    p = O.pointnet_init(N * C, 10, gen=torch.Generator().manual_seed(1))
+    h = O.pointnet_encode(p, x.view(B, N, C))
+    want_v, want_i = h.max(dim=1)
+    enc = [cu(p[k]) for k in ("mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "mlp.4.weight", "mlp.4.bias")]
+    feat = torch.empty(B, 512, device=DEV)
+    am = torch.empty(B, 512, device=DEV, dtype=torch.int32)
+    ops.pointnet_encode_forward(cu(x), N, C, enc, "tanh", "fp32", feat, None, am, None)
+    assert close(feat.cpu(), want_v, 1e-4, 1e-5)
+    am = am.cpu().long()
+    # the chosen point attains the max (within fp32 reorder noise) and, among the duplicates, is the first one
+    picked = h.gather(1, am[:, None, :]).squeeze(1)
+    assert float((picked - want_v).abs().max()) < 1e-5
+    dup = (am >= 100) & (am < 400)
+    assert bool((am[dup] == 100).all())
+    assert float((am == want_i).float().mean()) > 0.99
+
+
+@pytest.mark.parametrize("B", [1, 37])
+def test_pointnet_vs_oracle_random_batch(B):
+    from partmanip_b200.algorithms.algo_utils.network import PointNet
+    torch.manual_seed(B)
+    net = PointNet(3072, 10, dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False), 0)
+    w = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net.to(DEV)
+    x = torch.rand(B, 3072) * 2 - 1
+    wl = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    y_ref = O.pointnet_forward(wl, x.clone())
+    (y_ref * torch.arange(1, 11)).sum().backward()
+    y = net(cu(x))
+    (y * torch.arange(1, 11, device=DEV)).sum().backward()
+    assert close(y.detach().cpu(), y_ref.detach(), 1e-4, 1e-5)
+    for k, p in net.named_parameters():
+        v = wl[k].grad
+        tol = 1e-4 * float(v.abs().max()) + 1e-6
+        assert float((p.grad.cpu() - v).abs().max()) <= tol, k
+
+
+# ------------------------------------------------------------------------------------------------ full iterations
+class _ReplayEnv:
+    """Serves the env tensors recorded in a ppo_iter_* fixture (tests/golden/make_golden.py:FakeEnv)."""
+
+    def __init__(self, g, E, D, A):
+        self.g, self.t = g, 0
+        self.num_envs, self.num_actions, self.max_episode_length = E, A, 200
+        self.num_obs = {"obs": D, "proprio_state": 0}
+        self.train_test_flag = "train"
+        self.reset_succ = torch.zeros(E, dtype=torch.bool, device=DEV)
+        self.rew_buf = torch.zeros(E, device=DEV)
+        self.actions = []
+
+    def reset(self):
+        return {"obs": cu(self.g["env.obs"][0])}
+
+    def step(self, actions, save_image_path=None):
+        t = self.t
+        self.t += 1
+        self.actions.append(actions.clone())
+        self.rew_buf = cu(self.g["env.rew"][t])
+        self.reset_succ = cu(self.g["env.succ"][t])
+        return {"obs": cu(self.g["env.obs"][t + 1])}, self.rew_buf, cu(self.g["env.done"][t]), {"succ_rate": torch.zeros(1, device=DEV)}
+
+
+class _Logger:
+    save_ckpt_dir = save_video_dir = save_pose_dir = "/tmp/pm_b200_test"
+
+    def info(self, d, it):
+        self.last = d
+
+
+def _runner(name):
+    from partmanip_b200.algorithms import ppo
+    g = load_golden(name)
+    E, D, A, net, over = ITER_CASES[name]
+    cfg = ppo_cfg(E, net, device=DEV, **over)
+    env = _ReplayEnv(g, E, D, A)
+    r = ppo(env, cfg, _Logger())
+    r.actor_critic.load_state_dict(sub(g, "init"))
+    return g, cfg, env, r
+
+
+@pytest.mark.parametrize("name", list(ITER_CASES))
+def test_full_iteration_against_reference_recording(name):
+    g, cfg, env, r = _runner(name)
+    curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+    last_obs, last_values = r.collect(curr, None, eps=cu(g["eps"]))
+    st = r.storage
+    # ---- rollout outputs (actions, values, log-probs, mu) vs the reference's buffer
+    assert close(st.observations.cpu(), g["buf.observations"], 1e-4, 1e-4), max_err(st.observations.cpu(), g["buf.observations"])
+    assert close(st.mu.cpu(), g["buf.mu"], 1e-4, 1e-4), max_err(st.mu.cpu(), g["buf.mu"])
+    assert close(st.actions.cpu(), g["buf.actions"], 1e-4, 1e-4)
+    assert close(st.actions_log_prob.cpu(), g["buf.actions_log_prob"], 1e-4, 1e-4)
+    assert close(st.values.cpu(), g["buf.values"], 1e-4, 1e-4)
+    assert torch.equal(st.sigma.cpu(), g["buf.sigma"]) and torch.equal(st.dones.cpu(), g["buf.dones"])
+    assert torch.equal(st.rewards.cpu(), g["buf.rewards"]) and torch.equal(st.succs.cpu(), g["buf.succs"])
+    if cfg["tricks"]["use_state_norm"]:
+        ms = r.state_norm.running_ms
+        assert ms.n == int(g["rms.n"]) and close(ms.mean.cpu(), g["rms.mean"], 1e-5, 1e-6) and close(ms.std.cpu(), g["rms.std"], 1e-5, 1e-6)
+    # ---- GAE
+    st.compute_returns(last_values, cfg["gamma"], cfg["lam"])
+    assert close(st.returns.cpu(), g["buf.returns"], 1e-4, 1e-4)
+    assert close(st.advantages.cpu(), g["buf.advantages"], 1e-3, 2e-4), max_err(st.advantages.cpu(), g["buf.advantages"])
+    # ---- update: start from the reference's exact buffer so the comparison isolates the update kernels
+    for k in ("observations", "actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
+        getattr(st, k).copy_(cu(g["buf." + k]))
+    r.update(1)
+    log = r.log_dict
+    assert log["Train/kl_update_count"] == int(g["log.Train/kl_update_count"])
+    assert r.optimizer_actor.step_count == int(g["adam_actor.0.step"])
+    assert r.optimizer_critic.step_count == int(g["adam_critic.0.step"])
+    assert close(log["Train/surrogate_loss"], g["log.Train/surrogate_loss"], 1e-3, 1e-5)
+    assert close(log["Train/value_function_loss"], g["log.Train/value_function_loss"], 1e-3, 1e-5)
+    assert close(log["Train/kl"], g["log.Train/kl"], 1e-3, 1e-6) and close(log["Train/kl_max"], g["log.Train/kl_max"], 1e-3, 1e-6)
+    fin = sub(g, "final")
+    lr = cfg["lr"]
+    sd = {k: v.cpu() for k, v in r.actor_critic.state_dict().items()}
+    # Adam's early steps move every weight by ~lr whatever the gradient scale: compare post-update weights with an
+    # absolute tolerance that is a small fraction of the total displacement (40 steps * lr), as the oracle test does
+    for k, v in fin.items():
+        assert float((sd[k] - v).abs().max()) <= 0.02 * 40 * lr, (k, float((sd[k] - v).abs().max()))
+    assert math.isclose(float(sd["log_std"].exp().mean()), float(g["log.Train/mean_action_noise_std"]), rel_tol=1e-5)
+
+
+def test_checkpoint_roundtrip_and_reference_format(tmp_path):
+    g, cfg, env, r = _runner("ppo_iter_mlp_e64.npz")
+    curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+    _, last_values = r.collect(curr, None, eps=cu(g["eps"]))
+    r.storage.compute_returns(last_values, cfg["gamma"], cfg["lam"])
+    r.update(1)
+    r.save_ckpt_dir = str(tmp_path)
+    r.save(7)
+    ck = torch.load(tmp_path / "model_7.pth", map_location="cpu", weights_only=False)
+    assert set(ck) >= {"iteration", "model_state_dict", "optimizer_actor", "optimizer_critic", "total_steps", "tricks",
+                       "obs_mode", "model_cfg", "state_running_ms"}                                   # ppo.py:86-98
+    # torch.optim.Adam accepts the optimiser dicts (format compatibility with reference checkpoints)
+    ref_params = [torch.nn.Parameter(v.clone()) for k, v in ck["model_state_dict"].items() if k.startswith("actor.")]
+    ref_ls = torch.nn.Parameter(ck["model_state_dict"]["log_std"].clone())
+    opt = torch.optim.Adam([{"params": ref_params}, {"params": [ref_ls]}], lr=1.0)
+    opt.load_state_dict(ck["optimizer_actor"])
+    assert float(opt.state_dict()["state"][0]["step"]) == r.optimizer_actor.step_count
+    from partmanip_b200.algorithms import ppo
+    cfg2 = dict(cfg, resume=str(tmp_path / "model_7.pth"))
+    r2 = ppo(_ReplayEnv(g, 64, 37, 7), cfg2, _Logger())
+    for k, v in r.actor_critic.state_dict().items():
+        assert torch.equal(v, r2.actor_critic.state_dict()[k])
+    assert torch.equal(r.optimizer_actor.exp_avg, r2.optimizer_actor.exp_avg)
+    assert r2.optimizer_critic.step_count == r.optimizer_critic.step_count and r2.curr_iter == 7
+    assert torch.equal(r.state_norm.running_ms.mean, r2.state_norm.running_ms.mean)
+
+
+def test_storage_overflow_and_sampler_geometry():
+    from partmanip_b200.algorithms.algo_utils import RolloutStorage
+    st = RolloutStorage(4, 2, 5, 3, DEV, None)
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    for _ in range(2):
+        st.add_transitions(z(4, 5), z(4, 3), z(4), z(4).bool(), z(4).bool(), z(4, 1), z(4), z(4, 3), z(4, 3))
+    with pytest.raises(AssertionError, match="Rollout buffer overflow"):                           # storage.py:44-45
+        st.add_transitions(z(4, 5), z(4, 3), z(4), z(4).bool(), z(4).bool(), z(4, 1), z(4), z(4, 3), z(4, 3))
+    geo = load_golden("sampler_geometry.npz")["geo"]
+    for E, T, nmb, count, size, first, last in geo.tolist():
+        s2 = RolloutStorage(E, T, 1, 1, DEV, None)
+        b = s2.mini_batch_generator(nmb)
+        assert len(b) == count and len(b[0]) == size and b[0][0] == first and b[-1][-1] == last
+    s3 = RolloutStorage(64, 8, 1, 1, DEV, None, sampler="random")
+    idx = torch.cat(list(s3.mini_batch_generator(8)))
+    assert idx.numel() == 512 and torch.equal(idx.sort()[0].cpu(), torch.arange(512))
