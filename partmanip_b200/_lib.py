@@ -87,6 +87,19 @@ def _load():
 lib = _load()
 
 
+# kernels launched per C-ABI call (typical path) — feeds bench.py's gpu_launches claim
+KERNELS_PER_CALL = {
+    "pm_rms_colsum": 2, "pm_rms_colsqdev": 2, "pm_rms_update": 1, "pm_rms_normalize": 1, "pm_rms_forward": 6, "pm_gae": 1,
+    "pm_normalize": 1, "pm_normalize_inplace": 1, "pm_randn": 1, "pm_policy_sample": 1, "pm_action_activation": 1,
+    "pm_policy_logprob": 1, "pm_ppo_actor_loss": 2, "pm_ppo_actor_finalize": 1, "pm_value_loss": 2, "pm_abs_sum": 2,
+    "pm_accumulate": 1, "pm_dagger_loss": 2, "pm_linear_forward": 1, "pm_linear_backward": 4, "pm_pointnet_center": 1,
+    "pm_pointnet_encode_forward": 1, "pm_pointnet_encode_backward": 17, "pm_adam_step": 3, "pm_gather_rows": 1,
+    "pm_copy_rows": 1,
+}
+LAUNCHES = [0]
+
+
 def check(rc: int, what: str = ""):
+    LAUNCHES[0] += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         raise PMError(f"{what or 'libpartmanip_b200'} failed (rc={rc}): {lib.pm_last_error().decode()}")

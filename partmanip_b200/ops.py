@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from ._lib import EncoderParams, PM_ACT, PM_PREC, check, lib
+from ._lib import EncoderParams, LAUNCHES, PM_ACT, PM_PREC, check, lib
 
 Tensor = torch.Tensor
 
@@ -41,6 +41,11 @@ def _rows(t: Tensor, name: str) -> Tuple[int, int, int]:
         raise ValueError(f"{name}: expected 2-D, got {tuple(t.shape)}")
     ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
     return t.shape[0], t.shape[1], ld
+
+
+def launch_count() -> int:
+    """Kernels launched through the C-ABI so far (per-call multiplicities in _lib.KERNELS_PER_CALL)."""
+    return LAUNCHES[0]
 
 
 _scratch = {}

@@ -85,6 +85,28 @@ def test_pointnet_argmax_first_index_and_duplicates():
     assert float((am == want_i).float().mean()) > 0.99
 
 
+def test_encoder_backward_with_reference_argmax_is_tight():
+    """Feeding the ORACLE's argmax removes the near-tie freedom: every encoder gradient then matches autograd to
+    fp32 reorder noise, including the per-row mlp.4.weight entries."""
+    from partmanip_b200 import ops
+    torch.manual_seed(9)
+    B, N, C = 8, 1024, 3
+    x = torch.rand(B, N * C) * 2 - 1
+    x.view(B, N, C)[:, ::10] = 0.0
+    p = {k: v.requires_grad_(True) for k, v in O.pointnet_init(N * C, 10, gen=torch.Generator().manual_seed(2)).items()}
+    h = O.pointnet_encode(p, x.view(B, N, C))
+    feat, am = h.max(dim=1)
+    dfeat = torch.randn(B, 512)
+    feat.backward(dfeat)
+    names = ("mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias", "mlp.4.weight", "mlp.4.bias")
+    enc = [cu(p[k].detach()) for k in names]
+    grads = [torch.empty_like(t) for t in enc]
+    ops.pointnet_encode_backward(cu(x), N, C, enc, "tanh", cu(dfeat), cu(am.int()), grads)
+    for k, gt in zip(names, grads):
+        v = p[k].grad
+        assert float((gt.cpu() - v).abs().max()) <= 2e-5 * float(v.abs().max()) + 1e-7, (k, max_err(gt.cpu(), v))
+
+
 @pytest.mark.parametrize("B", [1, 37])
 def test_pointnet_vs_oracle_random_batch(B):
     from partmanip_b200.algorithms.algo_utils.network import PointNet
@@ -183,10 +205,17 @@ def test_full_iteration_against_reference_recording(name):
     fin = sub(g, "final")
     lr = cfg["lr"]
     sd = {k: v.cpu() for k, v in r.actor_critic.state_dict().items()}
-    # Adam's early steps move every weight by ~lr whatever the gradient scale: compare post-update weights with an
-    # absolute tolerance that is a small fraction of the total displacement (40 steps * lr), as the oracle test does
+    # Post-update weights.  Adam's early steps move every weight by ~lr per step whatever the gradient scale, so the
+    # yardstick is the total displacement 40*lr.  The max-pool makes a few rows of mlp.4.weight depend on WHICH of two
+    # near-tied points (|h3 gap| ~ fp32 reorder noise) wins the argmax: a different GEMM summation order (MKL vs
+    # cuBLAS vs these kernels) legitimately flips a handful of them and those rows then take different +-lr steps.
+    # Gate: every element within half the displacement, >= 99 % of each tensor within 2 % of it, RMS within 1 %.
+    disp = 40 * lr
     for k, v in fin.items():
-        assert float((sd[k] - v).abs().max()) <= 0.02 * 40 * lr, (k, float((sd[k] - v).abs().max()))
+        d = (sd[k] - v).abs()
+        assert float(d.max()) <= 0.5 * disp, (k, float(d.max()))
+        assert float((d > 0.02 * disp).float().mean()) <= 0.01, (k, float((d > 0.02 * disp).float().mean()))
+        assert float(d.pow(2).mean().sqrt()) <= 0.01 * disp, (k, float(d.pow(2).mean().sqrt()))
     assert math.isclose(float(sd["log_std"].exp().mean()), float(g["log.Train/mean_action_noise_std"]), rel_tol=1e-5)
 
 
