@@ -195,6 +195,9 @@ int pm_pointnet_encode_forward(const float* x, int64_t ldx, int B, int N, int C,
                                float* feat_mean, int64_t ldf, int32_t* argmax, float* h2mean,
                                void* ws, size_t ws_bytes, pm_stream_t s);
 size_t pm_pointnet_encode_forward_ws_bytes(int B, int N, int C, int precision);
+/* diagnostic for PM_PREC_BF16: the device-side protocol error word the last launch left in `ws`
+ * (0 = clean; 1xx = a bounded mbarrier wait expired).  Synchronises the stream. */
+int pm_pointnet_tc_last_error(const void* ws, pm_stream_t s);
 
 /* Backward through max-pool + per-point MLP.  The max-pool routes dfeat[b,c] to the single point
  * argmax[b,c], so only the unique "critical" points of each cloud carry gradient: their

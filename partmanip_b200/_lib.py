@@ -55,6 +55,7 @@ SIGNATURES = {
     "pm_pointnet_center": (I, [P, L, I, I, I, P]),
     "pm_pointnet_encode_forward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, P, SZ, P]),
     "pm_pointnet_encode_forward_ws_bytes": (SZ, [I, I, I, I]),
+    "pm_pointnet_tc_last_error": (I, [P, P]),
     "pm_pointnet_encode_backward_ws_bytes": (SZ, [I, I, I, I]),
     "pm_pointnet_encode_backward": (I, [P, L, I, I, I, EP, I, P, P, L, P, P, EP, P, SZ, P]),
     "pm_adam_ws_bytes": (SZ, [L]),

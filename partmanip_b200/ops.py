@@ -301,6 +301,14 @@ def pointnet_encode_forward(x: Tensor, N: int, C: int, enc_params: Sequence[Tens
           "pm_pointnet_encode_forward")
 
 
+def pointnet_tc_last_error(device) -> int:
+    """Protocol error word of the last bf16 encoder launch on `device` (0 = clean).  Synchronises."""
+    ws = _scratch.get((str(device), "encfwd"))
+    if ws is None:
+        return 0
+    return int(lib.pm_pointnet_tc_last_error(_p(ws), _stream()))
+
+
 def pointnet_encode_backward(x: Tensor, N: int, C: int, enc_params: Sequence[Tensor], act, dfeat: Tensor,
                              argmax: Tensor, enc_grads: Sequence[Tensor], dfeat_mean: Optional[Tensor] = None,
                              h2mean: Optional[Tensor] = None):
