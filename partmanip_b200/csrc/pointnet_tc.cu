@@ -54,11 +54,13 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok;
 }
+// (plain try_wait / arrive as in cutlass::arch::ClusterBarrier: an `.acquire.cluster` qualifier makes ptxas emit
+// CCTL.IVALL — an L1 invalidate — on every spin; measured 12x slowdown of the whole kernel)
 // bounded wait: a protocol bug must surface as an error code, never as a hung GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* err, int code) {
   for (uint32_t spin = 0; spin < (1u << 22); ++spin)
@@ -69,7 +71,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t target_rank) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(target_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
