@@ -39,9 +39,13 @@ gemm_kernel(const GemmP p) {
   int M = p.M, K = p.K;
   int k_begin = 0, k_end = K;
   if (EPI == EPI_DW) {
-    if (p.lim_dev) K = min(K, *p.lim_dev);
-    k_begin = blockIdx.z * p.k_per_split;
-    k_end = min(K, k_begin + p.k_per_split);
+    int kps = p.k_per_split;
+    if (p.lim_dev) {   // spread the VALID rows over all splits (the static bound can be 5-10x the live row count)
+      K = min(K, *p.lim_dev);
+      kps = ((K + (int)gridDim.z - 1) / (int)gridDim.z + BK - 1) / BK * BK;
+    }
+    k_begin = blockIdx.z * kps;
+    k_end = min(K, k_begin + kps);
   } else {
     if (p.lim_dev) M = min(M, *p.lim_dev);
     if (m0 >= M) return;

@@ -63,6 +63,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // CCTL.IVALL — an L1 invalidate — on every spin; measured 12x slowdown of the whole kernel)
 // bounded wait: a protocol bug must surface as an error code, never as a hung GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* err, int code) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin)
     if (mbar_try_wait(bar, parity)) return true;
   if (err) atomicExch(err, code);
@@ -112,9 +113,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float act_fast(int act, float x) {
-  if (act == PM_ACT_TANH) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-  return pm_act_fwd(act, x);
+// compile-time activation: a runtime switch inside the unrolled per-element loops bloated the kernel to 330 KB of
+// SASS and made it instruction-fetch bound (ncu: stall_no_inst dominant, 100K cycles per tile instead of ~10K)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if (ACT == PM_ACT_TANH) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  if (ACT == PM_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == PM_ACT_LRELU) return x > 0.f ? x : 0.01f * x;
+  if (ACT == PM_ACT_NONE) return x;
+  return pm_act_fwd(ACT, x);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
@@ -152,12 +159,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ W2, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------ the encoder
-template <bool WANT_ARGMAX>
+template <int ACT, bool WANT_ARGMAX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, const uint8_t* __restrict__ wpack,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ b2,
-               const float* __restrict__ b3, int act, float* __restrict__ feat, int64_t ldf,
+               const float* __restrict__ b3, float* __restrict__ feat, int64_t ldf,
                int32_t* __restrict__ argmax, int32_t* __restrict__ err) {
+#ifdef PM_TC_TIMING
+  long long* dbg = reinterpret_cast<long long*>(err + 16);
+#define TSTAMP(slot) do { if (blockIdx.x < 2 && it == 3) dbg[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#else
+#define TSTAMP(slot) do { } while (0)
+#endif
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,6 +222,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     for (int b = cluster_id; b < B && ok; b += n_clusters) {
       for (int j = 0; j < tiles_per_cloud && ok; ++j, ++it) {
         const float* xp = x + (int64_t)b * ldx + (int64_t)(j * PTS_PER_TILE + rank * PTS_PER_CTA + row) * C;
+        if (tid == 0) TSTAMP(0);
         float xv[4] = {0.f, 0.f, 0.f, 0.f};
         for (int c = 0; c < C; ++c) xv[c] = __ldg(xp + c);
         // ---- layer 1 into registers (overlaps the tail of the previous tile's L3 MMAs)
@@ -219,11 +233,13 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
           const float4 w1 = *reinterpret_cast<const float4*>(sW1 + (2 * q + 1) * 4);
           const float a0 = fmaf(xv[3], w0.w, fmaf(xv[2], w0.z, fmaf(xv[1], w0.y, fmaf(xv[0], w0.x, sB1[2 * q]))));
           const float a1 = fmaf(xv[3], w1.w, fmaf(xv[2], w1.z, fmaf(xv[1], w1.y, fmaf(xv[0], w1.x, sB1[2 * q + 1]))));
-          h1[q] = pack_bf16(act_fast(act, a0), act_fast(act, a1));
+          h1[q] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
         }
         // the H region is still being read by the previous tile's layer-3 MMAs
+        if (tid == 0) TSTAMP(1);
         if (it > 0) ok = mbar_wait(bar(BAR_L3_DONE), (it - 1) & 1, err, 101);
         if (!ok) break;
+        if (tid == 0) TSTAMP(2);
 #pragma unroll
         for (int c16 = 0; c16 < 16; ++c16) {                  // 16 chunks of 8 channels; k-block = c16 / 8
           const uint32_t off = SM_H + (c16 >> 3) * KBLOCK_BYTES + sw128(row, c16 & 7);
@@ -232,10 +248,12 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         fence_proxy_async();
         named_bar_sync(1, 128);
         if (tid == 0) mbar_arrive_cluster(bar(BAR_H1_FULL), 0);
+        if (tid == 0) TSTAMP(3);
         // ---- layer-2 epilogue: acc2 row -> +b2 -> act -> bf16 -> H2 row
         ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 102);
         if (!ok) break;
         tc_fence_after();
+        if (tid == 0) TSTAMP(4);
 #pragma unroll 1
         for (int cc = 0; cc < 8; ++cc) {                      // 8 x 32 channels
           uint32_t v[32];
@@ -246,7 +264,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
           for (int i = 0; i < 16; ++i) {
             const float a0 = __uint_as_float(v[2 * i]) + __ldg(b2 + cc * 32 + 2 * i);
             const float a1 = __uint_as_float(v[2 * i + 1]) + __ldg(b2 + cc * 32 + 2 * i + 1);
-            pk[i] = pack_bf16(act_fast(act, a0), act_fast(act, a1));
+            pk[i] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -258,6 +276,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         fence_proxy_async();
         named_bar_sync(1, 128);
         if (tid == 0) mbar_arrive_cluster(bar(BAR_H2_FULL), 0);
+        if (tid == 0) TSTAMP(5);
       }
     }
   } else if (warp < 8) {
@@ -272,9 +291,11 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
 #pragma unroll 1
         for (int s = 0; s < 4 && ok; ++s) {
           const int buf = s & 1, chunk = s >> 1, half = s & 1;
+          if (tid == 128) TSTAMP(8 + 3 * s);
           ok = mbar_wait(bar(BAR_ACC3_FULL0 + buf), (it * 2 + chunk) & 1, err, 103);
           if (!ok) break;
           tc_fence_after();
+          if (tid == 128) TSTAMP(9 + 3 * s);
           float bv = best[chunk];
           int bi = besti[chunk];
 #pragma unroll 1
@@ -300,6 +321,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
           tc_fence_before();
           named_bar_sync(2, 128);
           if (tid == 128) mbar_arrive_cluster(bar(BAR_ACC3_EMPTY0 + buf), 0);
+          if (tid == 128) TSTAMP(10 + 3 * s);
         }
       }
       if (ok) {
@@ -317,9 +339,11 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     uint32_t it = 0;
     for (int b = cluster_id; b < B && ok; b += n_clusters) {
       for (int j = 0; j < tiles_per_cloud && ok; ++j, ++it) {
+        if (lane == 0) TSTAMP(24);
         ok = mbar_wait(bar(BAR_H1_FULL), it & 1, err, 104);
         if (!ok) break;
         tc_fence_after();
+        if (lane == 0) TSTAMP(25);
         if (lane == 0) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {                       // K = 128 = 2 k-blocks x 4 x UMMA_K(16)
@@ -329,15 +353,18 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
           umma_commit_mc(bar(BAR_ACC2_FULL));
         }
         __syncwarp();
+        if (lane == 0) TSTAMP(26);
         ok = mbar_wait(bar(BAR_H2_FULL), it & 1, err, 105);
         if (!ok) break;
         tc_fence_after();
+        if (lane == 0) TSTAMP(27);
 #pragma unroll 1
         for (int s = 0; s < 4 && ok; ++s) {
           const int buf = s & 1, chunk = s >> 1, half = s & 1;
           ok = mbar_wait(bar(BAR_ACC3_EMPTY0 + buf), ((it * 2 + chunk) & 1) ^ 1, err, 106);
           if (!ok) break;
           tc_fence_after();
+          if (lane == 0) TSTAMP(28 + 2 * s);
           if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {                    // K = 256 = 4 k-blocks x 4 x UMMA_K
@@ -349,6 +376,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
             if (s == 3) umma_commit_mc(bar(BAR_L3_DONE));
           }
           __syncwarp();
+          if (lane == 0) TSTAMP(29 + 2 * s);
         }
       }
     }
@@ -370,7 +398,7 @@ extern "C" {
 int pm_has_tcgen05(void) { return 1; }
 
 // workspace: two packed weight images (rank 0 / rank 1) + an error word
-size_t pm_pointnet_encode_forward_tc_ws_bytes(int, int, int) { return 2 * WPACK_PER_RANK + 256; }
+size_t pm_pointnet_encode_forward_tc_ws_bytes(int, int, int) { return 2 * WPACK_PER_RANK + 4096; }
 
 int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int C, const pm_encoder_params* p, int act,
                                   float* feat, int64_t ldf, int32_t* argmax, void* ws, size_t ws_bytes, pm_stream_t s) {
@@ -381,21 +409,35 @@ int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int
   cudaStream_t st = pm_st(s);
   uint8_t* wpack = reinterpret_cast<uint8_t*>(ws);
   int32_t* err = reinterpret_cast<int32_t*>(wpack + 2 * WPACK_PER_RANK);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(encoder_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    cudaError_t e2 = cudaFuncSetAttribute(encoder_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    attr_set = true;
-  }
   cudaMemsetAsync(err, 0, sizeof(int32_t), st);
   pack_weights_kernel<<<64, 256, 0, st>>>(p->W2, p->W3, wpack);
   int n_clusters = B < PM_NUM_SMS / 2 ? B : PM_NUM_SMS / 2;
   dim3 grid(2 * n_clusters);
-  if (argmax)
-    encoder_fwd_tc<true><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, act, feat, ldf, argmax, err);
-  else
-    encoder_fwd_tc<false><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, act, feat, ldf, nullptr, err);
+#define PM_TC_LAUNCH(ACTV)                                                                                                  \
+  case ACTV: {                                                                                                              \
+    static bool attr_set = false;                                                                                           \
+    if (!attr_set) {                                                                                                        \
+      cudaError_t e1 = cudaFuncSetAttribute(encoder_fwd_tc<ACTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);  \
+      cudaError_t e2 = cudaFuncSetAttribute(encoder_fwd_tc<ACTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL); \
+      if (e1 != cudaSuccess || e2 != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); \
+      attr_set = true;                                                                                                      \
+    }                                                                                                                       \
+    if (argmax)                                                                                                             \
+      encoder_fwd_tc<ACTV, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, argmax, err); \
+    else                                                                                                                    \
+      encoder_fwd_tc<ACTV, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, nullptr, err); \
+  } break;
+  switch (act) {
+    PM_TC_LAUNCH(PM_ACT_TANH)
+    PM_TC_LAUNCH(PM_ACT_RELU)
+    PM_TC_LAUNCH(PM_ACT_ELU)
+    PM_TC_LAUNCH(PM_ACT_SELU)
+    PM_TC_LAUNCH(PM_ACT_LRELU)
+    PM_TC_LAUNCH(PM_ACT_SIGMOID)
+    PM_TC_LAUNCH(PM_ACT_NONE)
+    default: PM_FAIL(PM_ERR_ARG, "bf16 encoder: activation %d", act);
+  }
+#undef PM_TC_LAUNCH
   PM_CHECK_LAUNCH("pm_pointnet_encode_forward_tc");
   return PM_OK;
 }
