@@ -203,13 +203,17 @@ int pm_pointnet_tc_last_error(const void* ws, pm_stream_t s);
  * argmax[b,c], so only the unique "critical" points of each cloud carry gradient: their
  * activations are recomputed from the 4C-byte inputs and layers 3..1 are back-propagated over
  * those rows only.  Identical to autograd's result.  dfeat_mean != NULL adds the
- * dense mean-pool branch (max_mean=True).  Gradients are OVERWRITTEN. */
-size_t pm_pointnet_encode_backward_ws_bytes(int B, int N, int C, int with_mean);
+ * dense mean-pool branch (max_mean=True).  Gradients are OVERWRITTEN.
+ * PM_PREC_BF16: one fused tcgen05 kernel that treats every (cloud, channel) pair as a row (bf16 operands,
+ * fp32 accumulation in TMEM / registers), then a fixed-order reduce of per-CTA partials. */
+size_t pm_pointnet_encode_backward_ws_bytes(int B, int N, int C, int with_mean, int precision);
 int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C,
-                                const pm_encoder_params* p, int act, const float* dfeat,
+                                const pm_encoder_params* p, int act, int precision, const float* dfeat,
                                 const float* dfeat_mean, int64_t lddf, const int32_t* argmax,
                                 const float* h2mean, const pm_encoder_grads* g, void* ws,
                                 size_t ws_bytes, pm_stream_t s);
+/* diagnostic for PM_PREC_BF16 backward: protocol error word of the last launch (0 = clean).  Synchronises. */
+int pm_pointnet_bwd_tc_last_error(const void* ws, pm_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
  * K7  grad-norm clip + Adam on flat buffers

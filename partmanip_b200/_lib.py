@@ -56,8 +56,9 @@ SIGNATURES = {
     "pm_pointnet_encode_forward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, P, SZ, P]),
     "pm_pointnet_encode_forward_ws_bytes": (SZ, [I, I, I, I]),
     "pm_pointnet_tc_last_error": (I, [P, P]),
-    "pm_pointnet_encode_backward_ws_bytes": (SZ, [I, I, I, I]),
-    "pm_pointnet_encode_backward": (I, [P, L, I, I, I, EP, I, P, P, L, P, P, EP, P, SZ, P]),
+    "pm_pointnet_encode_backward_ws_bytes": (SZ, [I, I, I, I, I]),
+    "pm_pointnet_encode_backward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, EP, P, SZ, P]),
+    "pm_pointnet_bwd_tc_last_error": (I, [P, P]),
     "pm_adam_ws_bytes": (SZ, [L]),
     "pm_adam_step": (I, [P, P, P, P, L, L, F, F, F, F, P, P, P, P]),
     "pm_gather_rows": (I, [P, L, P, P, L, L, I, P]),

@@ -169,8 +169,9 @@ class _PointNetRunner(_Runner):
         ops.linear_backward(buf["h1"], f[2].weight, buf["dh2"], grads[8], grads[9], buf["dh1"], net.act_name)
         ops.linear_backward(buf["feat"], f[0].weight, buf["dh1"], grads[6], grads[7], buf["dfeat"], None)
         dfm = buf["dfeat"][:, 512:1024] if net.max_mean_concat else None
+        prec = net.precision if not net.max_mean_concat else "fp32"
         ops.pointnet_encode_backward(x, N, C, self.enc_params(), net.act_name, buf["dfeat"][:, :512], buf["argmax"],
-                                     grads[0:6], dfm, buf["h2mean"])
+                                     grads[0:6], dfm, buf["h2mean"], precision=prec)
 
 
 class PointNet(nn.Module):

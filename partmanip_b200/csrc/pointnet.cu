@@ -14,6 +14,10 @@ extern "C" int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B,
                                              const pm_encoder_params* p, int act, float* feat, int64_t ldf,
                                              int32_t* argmax, void* ws, size_t ws_bytes, pm_stream_t s);
 extern "C" size_t pm_pointnet_encode_forward_tc_ws_bytes(int B, int N, int C);
+extern "C" int pm_pointnet_encode_backward_tc(const float* x, int64_t ldx, int B, int N, int C, const pm_encoder_params* p,
+                                              int act, const float* dfeat, int64_t lddf, const int32_t* argmax,
+                                              const pm_encoder_grads* g, void* ws, size_t ws_bytes, pm_stream_t s);
+extern "C" size_t pm_pointnet_encode_backward_tc_ws_bytes(int B, int N, int C);
 
 namespace {
 
@@ -475,16 +479,23 @@ int pm_pointnet_encode_forward(const float* x, int64_t ldx, int B, int N, int C,
   return PM_OK;
 }
 
-size_t pm_pointnet_encode_backward_ws_bytes(int B, int N, int C, int with_mean) {
+size_t pm_pointnet_encode_backward_ws_bytes(int B, int N, int C, int with_mean, int precision) {
+  if (precision == PM_PREC_BF16 && !with_mean) return pm_pointnet_encode_backward_tc_ws_bytes(B, N, C);
   return carve_bwd(nullptr, B, N, C, with_mean).total;
 }
 
 int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C, const pm_encoder_params* p, int act,
-                                const float* dfeat, const float* dfeat_mean, int64_t lddf, const int32_t* argmax,
-                                const float* h2mean, const pm_encoder_grads* g, void* ws, size_t ws_bytes,
-                                pm_stream_t s) {
+                                int precision, const float* dfeat, const float* dfeat_mean, int64_t lddf,
+                                const int32_t* argmax, const float* h2mean, const pm_encoder_grads* g, void* ws,
+                                size_t ws_bytes, pm_stream_t s) {
   PM_REQUIRE(x && p && dfeat && argmax && g && ws, PM_ERR_ARG, "pm_pointnet_encode_backward: null pointer");
   PM_REQUIRE(B > 0 && N > 0 && N <= 8192 && C >= 1 && C <= CMAX, PM_ERR_SHAPE, "pm_pointnet_encode_backward: B=%d N=%d C=%d", B, N, C);
+  PM_REQUIRE(act >= PM_ACT_NONE && act <= PM_ACT_SIGMOID, PM_ERR_ARG, "pm_pointnet_encode_backward: activation %d", act);
+  if (precision == PM_PREC_BF16) {
+    PM_REQUIRE(!dfeat_mean, PM_ERR_UNSUPPORTED, "bf16 encoder backward: max_mean pooling runs in PM_PREC_FP32 only");
+    return pm_pointnet_encode_backward_tc(x, ldx, B, N, C, p, act, dfeat, lddf, argmax, g, ws, ws_bytes, s);
+  }
+  PM_REQUIRE(precision == PM_PREC_FP32, PM_ERR_ARG, "pm_pointnet_encode_backward: precision %d", precision);
   PM_REQUIRE(!dfeat_mean, PM_ERR_UNSUPPORTED, "pm_pointnet_encode_backward: mean-pool branch (max_mean=True) backward not built yet");
   (void)h2mean;
   const int with_mean = dfeat_mean != nullptr;

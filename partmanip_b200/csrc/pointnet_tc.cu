@@ -16,10 +16,10 @@
 //   E3  4 warps    : lane = channel, columns = points: running max (+ first-index argmax) entirely in registers —
 //                    the transposed orientation makes the symmetric max-pool a per-thread reduction, no shuffles.
 // The (points x 128/256/512) activations never leave the SM; HBM sees 4C bytes per point in and 4 KB per cloud out.
-#include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace {
+using namespace pmtc;
 
 constexpr int TC_THREADS = 288;          // warps 0-3: L1 + E2 | warps 4-7: E3 | warp 8: TMEM alloc + MMA issue
 constexpr int PTS_PER_CTA = 128;
@@ -40,96 +40,6 @@ enum { BAR_H1_FULL = 0, BAR_ACC2_FULL, BAR_H2_FULL, BAR_ACC3_FULL0, BAR_ACC3_FUL
 
 // packed weight image per network, per CTA rank: [W3 half (131072) | W2 half (32768)] ready to memcpy into smem
 constexpr size_t WPACK_PER_RANK = 131072 + 32768;
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok;
-}
-// (plain try_wait / arrive as in cutlass::arch::ClusterBarrier: an `.acquire.cluster` qualifier makes ptxas emit
-// CCTL.IVALL — an L1 invalidate — on every spin; measured 12x slowdown of the whole kernel)
-// bounded wait: a protocol bug must surface as an error code, never as a hung GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* err, int code) {
-#pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-    if (mbar_try_wait(bar, parity)) return true;
-  if (err) atomicExch(err, code);
-  return false;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t target_rank) {
-  uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(target_rank));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(z) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024B |
-// version=1 | layout_type=2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D=f32, A=B=bf16, both K-major, dense
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// compile-time activation: a runtime switch inside the unrolled per-element loops bloated the kernel to 330 KB of
-// SASS and made it instruction-fetch bound (ncu: stall_no_inst dominant, 100K cycles per tile instead of ~10K)
-template <int ACT>
-__device__ __forceinline__ float act_fast(float x) {
-  if (ACT == PM_ACT_TANH) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-  if (ACT == PM_ACT_RELU) return fmaxf(x, 0.f);
-  if (ACT == PM_ACT_LRELU) return x > 0.f ? x : 0.01f * x;
-  if (ACT == PM_ACT_NONE) return x;
-  return pm_act_fwd(ACT, x);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-// byte offset of 16-byte chunk `c8` (0..7) of row `row` inside a 128-row, 64-element k-block (SWIZZLE_128B)
-__device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t c8) { return row * 128u + ((c8 ^ (row & 7u)) << 4); }
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // fp32 W2 (256,128) / W3 (512,256) -> bf16 smem images for CTA rank 0 and 1

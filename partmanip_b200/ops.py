@@ -309,17 +309,26 @@ def pointnet_tc_last_error(device) -> int:
     return int(lib.pm_pointnet_tc_last_error(_p(ws), _stream()))
 
 
+def pointnet_bwd_tc_last_error(device) -> int:
+    """Protocol error word of the last bf16 encoder-backward launch on `device` (0 = clean).  Synchronises."""
+    ws = _scratch.get((str(device), "encbwd_bf16"))
+    if ws is None:
+        return 0
+    return int(lib.pm_pointnet_bwd_tc_last_error(_p(ws), _stream()))
+
+
 def pointnet_encode_backward(x: Tensor, N: int, C: int, enc_params: Sequence[Tensor], act, dfeat: Tensor,
                              argmax: Tensor, enc_grads: Sequence[Tensor], dfeat_mean: Optional[Tensor] = None,
-                             h2mean: Optional[Tensor] = None):
+                             h2mean: Optional[Tensor] = None, precision: str = "fp32"):
     """autograd of network.py:175-182 w.r.t. the six encoder tensors (gradients overwritten)."""
     B, width, ldx = _rows(_f32(x, "x"), "x")
     _, fw, lddf = _rows(_f32(dfeat, "dfeat"), "dfeat")
     assert fw == 512 and argmax.dtype == torch.int32 and argmax.is_contiguous()
-    nbytes = lib.pm_pointnet_encode_backward_ws_bytes(B, N, C, int(dfeat_mean is not None))
-    ws = scratch(nbytes, x.device, "encbwd")
+    prec = PM_PREC[precision]
+    nbytes = lib.pm_pointnet_encode_backward_ws_bytes(B, N, C, int(dfeat_mean is not None), prec)
+    ws = scratch(nbytes, x.device, "encbwd_bf16" if prec else "encbwd")
     ps, gs = _enc_struct(enc_params), _enc_struct(enc_grads)
-    check(lib.pm_pointnet_encode_backward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], _p(dfeat), _p(dfeat_mean), lddf,
+    check(lib.pm_pointnet_encode_backward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], prec, _p(dfeat), _p(dfeat_mean), lddf,
                                           _p(argmax), _p(h2mean), ct.byref(gs), _p(ws), nbytes, _stream()),
           "pm_pointnet_encode_backward")
 
