@@ -171,6 +171,29 @@ int pm_linear_backward(const float* x, int64_t ldx, const float* W, const float*
                        int act_prev, const int32_t* m_dev, void* ws, pm_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * K3b  fused PointNet head  Linear(F,128)-act-Linear(128,32)-act-Linear(32,out)   (network.py:152-159, 186-198)
+ * One launch forward (16 batch rows per CTA through all three layers in shared memory; h1[B,128] and
+ * h2[B,32] are kept for the backward), three launches backward.  out <= 32.  fp32.
+ * dfeat (may be NULL) receives d/d(feat) for the first dfeat_cols columns (the pooled part; the proprio
+ * tail is an input).  Gradients are OVERWRITTEN.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float *W0, *b0; /* (128,F),(128)    final_mlp.0 */
+  const float *W1, *b1; /* (32,128),(32)    final_mlp.2 */
+  const float *W2, *b2; /* (out,32),(out)   final_mlp.4 */
+} pm_head_params;
+typedef struct {
+  float *W0, *b0, *W1, *b1, *W2, *b2;
+} pm_head_grads;
+int pm_pointnet_head_forward(const float* feat, int64_t ldf, int B, int F, const pm_head_params* p, int out_dim,
+                             int act, float* h1, float* h2, float* out, int64_t ldo, pm_stream_t s);
+size_t pm_pointnet_head_backward_ws_bytes(int B, int F);
+int pm_pointnet_head_backward(const float* feat, int64_t ldf, int B, int F, const pm_head_params* p, int out_dim,
+                              int act, const float* h1, const float* h2, const float* dout, int64_t lddo,
+                              const pm_head_grads* g, float* dfeat, int64_t lddf, int dfeat_cols, void* ws,
+                              size_t ws_bytes, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * K1/K2  PointNet encoder: per-point MLP C->128->256->512 + symmetric pooling
  * replaces network.py:165-182 (forward up to the pooled feature) and its autograd backward.
  * ------------------------------------------------------------------------------------------ */

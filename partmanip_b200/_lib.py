@@ -52,6 +52,9 @@ SIGNATURES = {
     "pm_linear_forward": (I, [P, L, P, P, P, L, I, I, I, I, P, P]),
     "pm_linear_backward_ws_bytes": (SZ, [I, I, I]),
     "pm_linear_backward": (I, [P, L, P, P, L, P, P, P, L, I, I, I, I, P, P, P]),
+    "pm_pointnet_head_forward": (I, [P, L, I, I, EP, I, I, P, P, P, L, P]),
+    "pm_pointnet_head_backward_ws_bytes": (SZ, [I, I]),
+    "pm_pointnet_head_backward": (I, [P, L, I, I, EP, I, I, P, P, P, L, EP, P, L, I, P, SZ, P]),
     "pm_pointnet_center": (I, [P, L, I, I, I, P]),
     "pm_pointnet_encode_forward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, P, SZ, P]),
     "pm_pointnet_encode_forward_ws_bytes": (SZ, [I, I, I, I]),
@@ -95,7 +98,8 @@ KERNELS_PER_CALL = {
     "pm_normalize": 1, "pm_normalize_inplace": 1, "pm_randn": 1, "pm_policy_sample": 1, "pm_action_activation": 1,
     "pm_policy_logprob": 1, "pm_ppo_actor_loss": 2, "pm_ppo_actor_finalize": 1, "pm_value_loss": 2, "pm_abs_sum": 2,
     "pm_accumulate": 1, "pm_dagger_loss": 2, "pm_linear_forward": 1, "pm_linear_backward": 4, "pm_pointnet_center": 1,
-    "pm_pointnet_encode_forward": 1, "pm_pointnet_encode_backward": 17, "pm_adam_step": 3, "pm_gather_rows": 1,
+    "pm_pointnet_encode_forward": 2, "pm_pointnet_encode_backward": 3, "pm_pointnet_head_forward": 1,
+    "pm_pointnet_head_backward": 3, "pm_adam_step": 3, "pm_gather_rows": 1,
     "pm_copy_rows": 1,
 }
 LAUNCHES = [0]

@@ -15,6 +15,8 @@ import torch.nn as nn
 
 from ... import ops
 
+import os
+_FUSED_HEAD = os.environ.get("PM_GENERIC_HEAD", "0") != "1"   # dev A/B switch: generic per-layer GEMM kernels instead
 _ACT_NAMES = ("elu", "selu", "relu", "crelu", "lrelu", "tanh", "sigmoid")
 
 
@@ -139,6 +141,10 @@ class _PointNetRunner(_Runner):
         m = self.net.mlp
         return [m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias]
 
+    def head_params(self):
+        f = self.net.final_mlp
+        return [f[0].weight, f[0].bias, f[2].weight, f[2].bias, f[4].weight, f[4].bias]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         net = self.net
         B = x.shape[0]
@@ -154,6 +160,9 @@ class _PointNetRunner(_Runner):
         if p:
             ops.copy_rows(x[:, N * C:N * C + p], feat[:, net.feat_dim - p:])
         f = net.final_mlp
+        if net.output_dim <= 32 and _FUSED_HEAD:      # fused head: one launch
+            return ops.pointnet_head_forward(feat, self.head_params(), net.output_dim, net.act_name, buf["h1"], buf["h2"],
+                                             buf["out"])
         ops.linear_forward(feat, f[0].weight, f[0].bias, net.act_name, out=buf["h1"])
         ops.linear_forward(buf["h1"], f[2].weight, f[2].bias, net.act_name, out=buf["h2"])
         return ops.linear_forward(buf["h2"], f[4].weight, f[4].bias, None, out=buf["out"])
@@ -165,9 +174,13 @@ class _PointNetRunner(_Runner):
         N, C = net.point_num, net.in_channels
         buf = self._get(B, x.device)
         f = net.final_mlp
-        ops.linear_backward(buf["h2"], f[4].weight, dout, grads[10], grads[11], buf["dh2"], net.act_name)
-        ops.linear_backward(buf["h1"], f[2].weight, buf["dh2"], grads[8], grads[9], buf["dh1"], net.act_name)
-        ops.linear_backward(buf["feat"], f[0].weight, buf["dh1"], grads[6], grads[7], buf["dfeat"], None)
+        if net.output_dim <= 32 and _FUSED_HEAD:      # fused head backward: three launches
+            ops.pointnet_head_backward(buf["feat"], self.head_params(), net.output_dim, net.act_name, buf["h1"], buf["h2"],
+                                       dout, grads[6:12], buf["dfeat"], 512 * (1 + net.max_mean_concat))
+        else:
+            ops.linear_backward(buf["h2"], f[4].weight, dout, grads[10], grads[11], buf["dh2"], net.act_name)
+            ops.linear_backward(buf["h1"], f[2].weight, buf["dh2"], grads[8], grads[9], buf["dh1"], net.act_name)
+            ops.linear_backward(buf["feat"], f[0].weight, buf["dh1"], grads[6], grads[7], buf["dfeat"], None)
         dfm = buf["dfeat"][:, 512:1024] if net.max_mean_concat else None
         prec = net.precision if not net.max_mean_concat else "fp32"
         ops.pointnet_encode_backward(x, N, C, self.enc_params(), net.act_name, buf["dfeat"][:, :512], buf["argmax"],

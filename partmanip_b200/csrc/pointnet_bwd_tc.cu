@@ -152,24 +152,28 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     for (int i = 0; i < 128; ++i) acc3[i] = 0.f;
     float db3 = 0.f, db2 = 0.f, dw1[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f;
 
-    auto load_row = [&](int pair, float& g, float (&xv)[4]) {
+    // statically indexed (C <= 4 predicated loads) so the prefetched values stay in registers and in flight
+    auto load_row = [&](int pair, float& g, float& x0, float& x1, float& x2, float& x3) {
       const int b = 2 * pair + par;
-      g = 0.f; xv[0] = xv[1] = xv[2] = xv[3] = 0.f;
+      g = 0.f; x0 = x1 = x2 = x3 = 0.f;
       if (b < B) {
         int n = __ldg(argmax + (int64_t)b * 512 + c);
         n = min(max(n, 0), N - 1);
         g = __ldg(dfeat + (int64_t)b * lddf + c);
         const float* xp = x + (int64_t)b * ldx + (int64_t)n * C;
-        for (int cc = 0; cc < C; ++cc) xv[cc] = __ldg(xp + cc);
+        x0 = __ldg(xp);
+        if (C > 1) x1 = __ldg(xp + 1);
+        if (C > 2) x2 = __ldg(xp + 2);
+        if (C > 3) x3 = __ldg(xp + 3);
       }
     };
-    float g_nxt, xv_nxt[4];
-    if (n_tiles > 0) load_row(slab, g_nxt, xv_nxt);
+    float g_nxt = 0.f, xn0 = 0.f, xn1 = 0.f, xn2 = 0.f, xn3 = 0.f;
+    if (n_tiles > 0) load_row(slab, g_nxt, xn0, xn1, xn2, xn3);
 
     for (int it = 0; it < n_tiles && ok; ++it) {
       const float g = g_nxt;
-      float xv[4] = {xv_nxt[0], xv_nxt[1], xv_nxt[2], xv_nxt[3]};
-      if (it + 1 < n_tiles) load_row(slab + (it + 1) * n_slabs, g_nxt, xv_nxt);   // prefetch the next tile's row
+      const float xv[4] = {xn0, xn1, xn2, xn3};
+      if (it + 1 < n_tiles) load_row(slab + (it + 1) * n_slabs, g_nxt, xn0, xn1, xn2, xn3);   // prefetch the next tile's row
       // ---- S1: layer 1 for this thread's 64 channels (= one k-block of H1)
       {
         uint32_t h1[32];

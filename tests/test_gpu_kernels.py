@@ -298,3 +298,32 @@ def test_kat1_shipped_checkpoint_through_actor_critic(ops):
     assert close(mu.cpu(), g["mu"], 1e-4, 1e-4) and torch.equal(sig.cpu(), g["sigma"])
     # state_dict keys are the reference's
     assert set(ac.state_dict().keys()) == set(sub(g, "w").keys())
+
+
+@pytest.mark.parametrize("B,F,out,act,cols", [(2048, 512, 10, "tanh", 512), (37, 537, 1, "elu", 512), (5, 1024, 7, "relu", 1024),
+                                              (300, 512, 32, "tanh", 512), (1, 512, 10, "sigmoid", 512)])
+def test_fused_head_forward_backward_vs_torch(ops, B, F, out, act, cols):
+    """K3b: fused Linear(F,128)-act-Linear(128,32)-act-Linear(32,out) against torch autograd (fp32 gate 1e-4)."""
+    torch.manual_seed(B + F + out)
+    f = {"tanh": torch.tanh, "elu": torch.nn.functional.elu, "relu": torch.relu, "sigmoid": torch.sigmoid}[act]
+    feat = torch.randn(B, F, requires_grad=True)
+    Ws = [(torch.randn(128, F) / F ** 0.5), torch.randn(128) * 0.1, torch.randn(32, 128) / 128 ** 0.5, torch.randn(32) * 0.1,
+          torch.randn(out, 32) / 32 ** 0.5, torch.randn(out) * 0.1]
+    Ws = [w.requires_grad_(True) for w in Ws]
+    h1 = f(feat @ Ws[0].T + Ws[1]); h2 = f(h1 @ Ws[2].T + Ws[3]); y = h2 @ Ws[4].T + Ws[5]
+    dout = torch.randn(B, out)
+    y.backward(dout)
+    dW = [cu(w.detach()) for w in Ws]
+    g = [torch.full_like(w, float("nan")) for w in dW]
+    h1d, h2d, yd = torch.empty(B, 128, device=DEV), torch.empty(B, 32, device=DEV), torch.empty(B, out, device=DEV)
+    featd = cu(feat.detach())
+    ops.pointnet_head_forward(featd, dW, out, act, h1d, h2d, yd)
+    assert close(yd.cpu(), y.detach(), 1e-4, 1e-5), max_err(yd.cpu(), y.detach())
+    assert close(h1d.cpu(), h1.detach(), 1e-4, 1e-5) and close(h2d.cpu(), h2.detach(), 1e-4, 1e-5)
+    dfeat = torch.full((B, cols), float("nan"), device=DEV)
+    ops.pointnet_head_backward(featd, dW, out, act, h1d, h2d, cu(dout), g, dfeat, cols)
+    for got, w in zip(g, Ws):
+        tol = 1e-4 * float(w.grad.abs().max()) + 1e-6
+        assert float((got.cpu() - w.grad).abs().max()) <= tol, (tuple(w.shape), float((got.cpu() - w.grad).abs().max()), tol)
+    want = feat.grad[:, :cols]
+    assert float((dfeat.cpu() - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-6
