@@ -31,12 +31,16 @@ constexpr uint32_t SM_W2 = 131072;       // 2 k-blocks x (128 rows x 128 B)     
 constexpr uint32_t SM_H = 163840;        // H2: 4 k-blocks x (128 rows x 128 B) = 65536; H1 overlays the first 32768
 constexpr uint32_t SM_W1 = 229376;       // 128 x 4 fp32                                    =   2048
 constexpr uint32_t SM_B1 = 231424;       // 128 fp32                                        =    512
-constexpr uint32_t SM_BAR = 231936;      // 8 mbarriers (64 B) + tmem base (4 B)
+constexpr uint32_t SM_BAR = 231936;      // 13 mbarriers (104 B) + tmem base (4 B, at +112)
 constexpr uint32_t SM_TOTAL = 232064;
 constexpr uint32_t KBLOCK_BYTES = 128 * 128;   // one 64-wide k-block of a 128-row operand
 
-enum { BAR_H1_FULL = 0, BAR_ACC2_FULL, BAR_H2_FULL, BAR_ACC3_FULL0, BAR_ACC3_FULL1, BAR_ACC3_EMPTY0, BAR_ACC3_EMPTY1,
-       BAR_L3_DONE, NUM_BARS };
+enum { BAR_H1_FULL = 0, BAR_ACC2_FULL, BAR_H2_KB0, BAR_H2_KB1, BAR_H2_KB2, BAR_H2_KB3, BAR_ACC3_FULL0, BAR_ACC3_FULL1,
+       BAR_ACC3_FULL2, BAR_ACC3_EMPTY0, BAR_ACC3_EMPTY1, BAR_ACC3_EMPTY2, BAR_L3_DONE, NUM_BARS };
+// layer-3 accumulator of MMA group s (TMEM column base): groups 0/3 -> buffer 0 [256,384), group 1 -> buffer 1 [384,512),
+// group 2 -> the low half of the layer-2 accumulator [0,128), which is free once E2 has read it
+__host__ __device__ constexpr uint32_t acc3_col(int s) { return s == 2 ? 0u : (s == 1 ? 384u : 256u); }
+__host__ __device__ constexpr int acc3_bar(int s) { return s == 2 ? 2 : (s == 1 ? 1 : 0); }
 
 // packed weight image per network, per CTA rank: [W3 half (131072) | W2 half (32768)] ready to memcpy into smem
 constexpr size_t WPACK_PER_RANK = 131072 + 32768;
@@ -69,6 +73,55 @@ __global__ void pack_weights_kernel(const float* __restrict__ W2, const float* _
 }
 
 // ------------------------------------------------------------------------------------------------ the encoder
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// max of 32 values: 16 three-input FMNMX in 4 independent chains
+__device__ __forceinline__ float max32(const float (&k)[32]) {
+  float m0 = fmax3(k[0], k[1], k[2]), m1 = fmax3(k[3], k[4], k[5]), m2 = fmax3(k[6], k[7], k[8]), m3 = fmax3(k[9], k[10], k[11]);
+  m0 = fmax3(m0, k[12], k[13]); m1 = fmax3(m1, k[14], k[15]); m2 = fmax3(m2, k[16], k[17]); m3 = fmax3(m3, k[18], k[19]);
+  m0 = fmax3(m0, k[20], k[21]); m1 = fmax3(m1, k[22], k[23]); m2 = fmax3(m2, k[24], k[25]); m3 = fmax3(m3, k[26], k[27]);
+  m0 = fmax3(m0, k[28], k[29]); m1 = fmax3(m1, k[30], k[31]);
+  return fmax3(m0, m1, fmaxf(m2, m3));
+}
+
+// layer 1 for the 16-byte chunks [C0, C1) of this thread's point row: h[(c-C0)*4 + q] = bf16x2 of channels 8c+2q, 8c+2q+1
+template <int ACT, int C0, int C1>
+__device__ __forceinline__ void layer1_part(const float (&xv)[4], const float* sW1, const float* sB1, uint32_t (&h)[(C1 - C0) * 4]) {
+#pragma unroll
+  for (int q = C0 * 4; q < C1 * 4; ++q) {
+    const float4 w0 = *reinterpret_cast<const float4*>(sW1 + (2 * q) * 4);
+    const float4 w1 = *reinterpret_cast<const float4*>(sW1 + (2 * q + 1) * 4);
+    const float a0 = fmaf(xv[3], w0.w, fmaf(xv[2], w0.z, fmaf(xv[1], w0.y, fmaf(xv[0], w0.x, sB1[2 * q]))));
+    const float a1 = fmaf(xv[3], w1.w, fmaf(xv[2], w1.z, fmaf(xv[1], w1.y, fmaf(xv[0], w1.x, sB1[2 * q + 1]))));
+    h[q - C0 * 4] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
+  }
+}
+template <int C0, int C1>
+__device__ __forceinline__ void store_h1_part(uint8_t* smem, int row, const uint32_t (&h)[(C1 - C0) * 4]) {
+#pragma unroll
+  for (int c16 = C0; c16 < C1; ++c16) {
+    const uint32_t off = SM_H + (c16 >> 3) * KBLOCK_BYTES + sw128(row, c16 & 7);
+    *reinterpret_cast<uint4*>(smem + off) =
+        make_uint4(h[4 * (c16 - C0)], h[4 * (c16 - C0) + 1], h[4 * (c16 - C0) + 2], h[4 * (c16 - C0) + 3]);
+  }
+}
+__device__ __forceinline__ void load_point(const float* __restrict__ x, int64_t ldx, int C, int b, int pt, float (&xv)[4]) {
+  const float* xp = x + (int64_t)b * ldx + (int64_t)pt * C;
+  xv[0] = __ldg(xp);
+  xv[1] = C > 1 ? __ldg(xp + 1) : 0.f;
+  xv[2] = C > 2 ? __ldg(xp + 2) : 0.f;
+  xv[3] = C > 3 ? __ldg(xp + 3) : 0.f;
+}
+
+// Roles (288 threads): warps 0-3 "A": layer 1 (80 of 128 channels) + layer-2 epilogue | warps 4-7 "B": layer-3 epilogue
+// (max-pool) + the other 48 layer-1 channels of the NEXT tile | warp 8: TMEM alloc + MMA issue (leader CTA only).
+// Pipeline per 256-point tile (t):   H1(t) -> L2 MMA -> E2 writes H2 one 64-channel k-block at a time; the layer-3 MMAs of
+// the first channel chunk (both point halves, two TMEM buffers) are issued k-block by k-block BEHIND E2, so 2 of the 4
+// MMA groups run under the epilogue; the second chunk's groups reuse the buffers as soon as E3 has drained them.
 template <int ACT, bool WANT_ARGMAX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, const uint8_t* __restrict__ wpack,
@@ -86,11 +139,14 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int tiles_per_cloud = N / PTS_PER_TILE;
+  const int tpc = N / PTS_PER_TILE;                                   // tiles per cloud
+  const int n_clouds = cluster_id < B ? (B - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const int n_tiles = n_clouds * tpc;
   float* sW1 = reinterpret_cast<float*>(smem + SM_W1);
   float* sB1 = reinterpret_cast<float*>(smem + SM_B1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 112);
   auto bar = [&](int i) { return sbase + SM_BAR + 8u * i; };
+  auto tile_cloud = [&](int it) { return cluster_id + (it / tpc) * n_clusters; };
 
   // ---------------- prologue: resident weights, barriers, TMEM
   if ((sbase & 1023u) != 0 && tid == 0) atomicExch(err, 900);
@@ -104,11 +160,8 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   if (tid == 0) {
     mbar_init(bar(BAR_H1_FULL), 2);
     mbar_init(bar(BAR_ACC2_FULL), 1);
-    mbar_init(bar(BAR_H2_FULL), 2);
-    mbar_init(bar(BAR_ACC3_FULL0), 1);
-    mbar_init(bar(BAR_ACC3_FULL1), 1);
-    mbar_init(bar(BAR_ACC3_EMPTY0), 2);
-    mbar_init(bar(BAR_ACC3_EMPTY1), 2);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar(BAR_H2_KB0 + kb), 2);
+    for (int i = 0; i < 3; ++i) { mbar_init(bar(BAR_ACC3_FULL0 + i), 1); mbar_init(bar(BAR_ACC3_EMPTY0 + i), 2); }
     mbar_init(bar(BAR_L3_DONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -124,171 +177,234 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
 
-  if (warp < 4) {
-    // =========================================================== group A: layer 1 + layer-2 epilogue (thread = point row)
-    const int row = tid;                                      // 0..127 == TMEM lane
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t it = 0;
-    for (int b = cluster_id; b < B && ok; b += n_clusters) {
-      for (int j = 0; j < tiles_per_cloud && ok; ++j, ++it) {
-        const float* xp = x + (int64_t)b * ldx + (int64_t)(j * PTS_PER_TILE + rank * PTS_PER_CTA + row) * C;
-        if (tid == 0) TSTAMP(0);
-        float xv[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < C; ++c) xv[c] = __ldg(xp + c);
-        // ---- layer 1 into registers (overlaps the tail of the previous tile's L3 MMAs)
-        uint32_t h1[64];
+  // ---- layer-2 epilogue of one 128-column half of acc2 (two 64-channel k-blocks of H2): acc2 row -> +b2 -> act -> bf16 ->
+  //      smem, with the tcgen05.ld and the b2 loads of chunk c+1 in flight while chunk c is processed (b2 comes from L2: the
+  //      227 KB carve-out leaves almost no L1).  Groups A and B each take one half, so two warps per scheduler interleave
+  //      their MUFU.TANH streams with the other's FADD / pack / store work.
+  auto e2_half = [&](uint32_t lane_taddr, int row, int cc0, const float4 (&b0)[8], int bar_id, int tid0) {
+    auto e2_chunk = [&](const uint32_t (&v)[32], const float4 (&bb)[8], int cc) {
+      uint32_t pk[16];
 #pragma unroll
-        for (int q = 0; q < 64; ++q) {
-          const float4 w0 = *reinterpret_cast<const float4*>(sW1 + (2 * q) * 4);
-          const float4 w1 = *reinterpret_cast<const float4*>(sW1 + (2 * q + 1) * 4);
-          const float a0 = fmaf(xv[3], w0.w, fmaf(xv[2], w0.z, fmaf(xv[1], w0.y, fmaf(xv[0], w0.x, sB1[2 * q]))));
-          const float a1 = fmaf(xv[3], w1.w, fmaf(xv[2], w1.z, fmaf(xv[1], w1.y, fmaf(xv[0], w1.x, sB1[2 * q + 1]))));
-          h1[q] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
-        }
-        // the H region is still being read by the previous tile's layer-3 MMAs
-        if (tid == 0) TSTAMP(1);
-        if (it > 0) ok = mbar_wait(bar(BAR_L3_DONE), (it - 1) & 1, err, 101);
-        if (!ok) break;
-        if (tid == 0) TSTAMP(2);
-#pragma unroll
-        for (int c16 = 0; c16 < 16; ++c16) {                  // 16 chunks of 8 channels; k-block = c16 / 8
-          const uint32_t off = SM_H + (c16 >> 3) * KBLOCK_BYTES + sw128(row, c16 & 7);
-          *reinterpret_cast<uint4*>(smem + off) = make_uint4(h1[4 * c16], h1[4 * c16 + 1], h1[4 * c16 + 2], h1[4 * c16 + 3]);
-        }
-        fence_proxy_async();
-        named_bar_sync(1, 128);
-        if (tid == 0) mbar_arrive_cluster(bar(BAR_H1_FULL), 0);
-        if (tid == 0) TSTAMP(3);
-        // ---- layer-2 epilogue: acc2 row -> +b2 -> act -> bf16 -> H2 row
-        ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 102);
-        if (!ok) break;
-        tc_fence_after();
-        if (tid == 0) TSTAMP(4);
-#pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {                      // 8 x 32 channels
-          uint32_t v[32];
-          tmem_ld32(lane_taddr + cc * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float a0 = __uint_as_float(v[2 * i]) + __ldg(b2 + cc * 32 + 2 * i);
-            const float a1 = __uint_as_float(v[2 * i + 1]) + __ldg(b2 + cc * 32 + 2 * i + 1);
-            pk[i] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t off = SM_H + (cc >> 1) * KBLOCK_BYTES + sw128(row, (cc & 1) * 4 + q);
-            *reinterpret_cast<uint4*>(smem + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        named_bar_sync(1, 128);
-        if (tid == 0) mbar_arrive_cluster(bar(BAR_H2_FULL), 0);
-        if (tid == 0) TSTAMP(5);
+      for (int q = 0; q < 8; ++q) {
+        const float a0 = __uint_as_float(v[4 * q]) + bb[q].x, a1 = __uint_as_float(v[4 * q + 1]) + bb[q].y;
+        const float a2 = __uint_as_float(v[4 * q + 2]) + bb[q].z, a3 = __uint_as_float(v[4 * q + 3]) + bb[q].w;
+        pk[2 * q] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
+        pk[2 * q + 1] = pack_bf16(act_fast<ACT>(a2), act_fast<ACT>(a3));
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = SM_H + (cc >> 1) * KBLOCK_BYTES + sw128(row, (cc & 1) * 4 + q);
+        *reinterpret_cast<uint4*>(smem + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    };
+    auto load_b2 = [&](float4 (&bb)[8], int cc) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(b2 + cc * 32) + q);
+    };
+    uint32_t va[32], vb[32];
+    float4 ba[8], bbv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ba[q] = b0[q];
+    tmem_ld32(lane_taddr + cc0 * 32, va);
+    tmem_ld_wait();
+#pragma unroll 1
+    for (int kk = 0; kk < 2; ++kk) {                           // k-block (cc0/2 + kk) of H2 = chunks cc0+2kk, cc0+2kk+1
+      const int cc = cc0 + 2 * kk;
+      tmem_ld32(lane_taddr + (cc + 1) * 32, vb);
+      load_b2(bbv, cc + 1);
+      e2_chunk(va, ba, cc);
+      tmem_ld_wait();
+      if (kk == 0) { tmem_ld32(lane_taddr + (cc + 2) * 32, va); load_b2(ba, cc + 2); }
+      e2_chunk(vb, bbv, cc + 1);
+      if (kk == 0) tmem_ld_wait(); else tc_fence_before();
+      fence_proxy_async();                                     // release the k-block to the MMA warp
+      named_bar_sync(bar_id, 128);
+      if (tid == tid0) mbar_arrive_cluster(bar(BAR_H2_KB0 + (cc >> 1)), 0);
+    }
+  };
+
+  if (warp < 4) {
+    // =========================================================== group A: layer 1 + layer-2 epilogue of acc2 columns [0,128)
+    const int row = tid;                                      // 0..127 == TMEM lane == point row of this CTA
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};                       // next tile's point, fetched one tile ahead (HBM latency)
+    if (n_tiles > 0) load_point(x, ldx, C, tile_cloud(0), rank * PTS_PER_CTA + row, xn);
+    for (int it = 0; it < n_tiles && ok; ++it) {
+      if (tid == 0) TSTAMP(0);
+      const float xv[4] = {xn[0], xn[1], xn[2], xn[3]};
+      if (it + 1 < n_tiles) load_point(x, ldx, C, tile_cloud(it + 1), ((it + 1) % tpc) * PTS_PER_TILE + rank * PTS_PER_CTA + row, xn);
+      // layer 1 into registers while the previous tile's last layer-3 MMAs run
+      uint32_t h1[64];
+      layer1_part<ACT, 0, 16>(xv, sW1, sB1, h1);
+      if (tid == 0) TSTAMP(1);
+      // the H region is still being read by the previous tile's layer-3 MMAs
+      if (it > 0) ok = mbar_wait(bar(BAR_L3_DONE), (it - 1) & 1, err, 101);
+      if (!ok) break;
+      if (tid == 0) TSTAMP(2);
+      store_h1_part<0, 16>(smem, row, h1);
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (tid == 0) mbar_arrive_cluster(bar(BAR_H1_FULL), 0);
+      if (tid == 0) TSTAMP(3);
+      float4 ba0[8];                                          // b2 of the first chunk, in flight across the ACC2_FULL wait
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ba0[q] = __ldg(reinterpret_cast<const float4*>(b2) + q);
+      ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 102);
+      if (!ok) break;
+      tc_fence_after();
+      if (tid == 0) TSTAMP(4);
+      e2_half(lane_taddr, row, 0, ba0, 1, 0);
+      if (tid == 0) TSTAMP(5);
     }
   } else if (warp < 8) {
-    // =========================================================== group B: layer-3 epilogue (thread = output channel)
-    const int lrow = tid - 128;                               // 0..127 == TMEM lane
+    // =========================================================== group B: layer-2 epilogue of acc2 columns [128,256) (thread =
+    //                                                               point row), then the layer-3 epilogue (thread = output channel)
+    const int lrow = tid - 128;                               // 0..127 == TMEM lane == point row == channel within chunk
     const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
-    uint32_t it = 0;
-    for (int b = cluster_id; b < B && ok; b += n_clusters) {
-      float best[2] = {-INFINITY, -INFINITY};
-      int besti[2] = {0, 0};
-      for (int j = 0; j < tiles_per_cloud && ok; ++j, ++it) {
-#pragma unroll 1
-        for (int s = 0; s < 4 && ok; ++s) {
-          const int buf = s & 1, chunk = s >> 1, half = s & 1;
-          if (tid == 128) TSTAMP(8 + 3 * s);
-          ok = mbar_wait(bar(BAR_ACC3_FULL0 + buf), (it * 2 + chunk) & 1, err, 103);
-          if (!ok) break;
-          tc_fence_after();
-          if (tid == 128) TSTAMP(9 + 3 * s);
-          float bv = best[chunk];
-          int bi = besti[chunk];
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {                    // 4 x 32 columns (points)
-            uint32_t v[32];
-            tmem_ld32(lane_taddr + 256 + buf * 128 + cc * 32, v);
-            tmem_ld_wait();
+    float best[2] = {-INFINITY, -INFINITY};                   // running max (key when WANT_ARGMAX: low 5 bits = 31 - column)
+    int bestp[2] = {0, 0};                                    // point index of column 0 of the winning 32-column group
+    for (int it = 0; it < n_tiles && ok; ++it) {
+      const int b = tile_cloud(it), j = it % tpc;
+      {
+        float4 bb0[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bb0[q] = __ldg(reinterpret_cast<const float4*>(b2 + 128) + q);
+        if (tid == 128) TSTAMP(20);
+        ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 109);
+        if (!ok) break;
+        tc_fence_after();
+        e2_half(lane_taddr, lrow, 4, bb0, 2, 128);
+        if (tid == 128) TSTAMP(21);
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int chunk = s >> 1, half = s & 1;
+        if (tid == 128) TSTAMP(8 + 3 * s);
+        // buffer 0 completes two phases per tile (groups 0 and 3), buffers 1 and 2 one each
+        ok = mbar_wait(bar(BAR_ACC3_FULL0 + acc3_bar(s)), s == 0 ? 0u : (s == 3 ? 1u : (uint32_t)(it & 1)), err, 103);
+        if (!ok) break;
+        tc_fence_after();
+        if (tid == 128) TSTAMP(9 + 3 * s);
+        float bv = best[chunk];
+        int bp = bestp[chunk];
+        {
+          auto e3_chunk = [&](uint32_t (&v)[32], int cc) {      // 32 columns (points) of this thread's channel
             if (WANT_ARGMAX) {
+              // key = value with its low 5 mantissa bits replaced by (31 - column): one FMNMX tree yields max AND position
+              // (values closer than 2^-18 relative may swap order — far below the bf16 operand rounding)
+              float k[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) k[i] = __uint_as_float((v[i] & 0xFFFFFFE0u) | (uint32_t)(31 - i));
+              const float m = max32(k);
               // column n -> point: columns [0,64) come from CTA 0's rows, [64,128) from CTA 1's (B operand N halves)
               const int pbase = j * PTS_PER_TILE + (cc >> 1) * PTS_PER_CTA + half * 64 + (cc & 1) * 32;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float f = __uint_as_float(v[i]);
-                if (f > bv) { bv = f; bi = pbase + i; }
-              }
+              if (m > bv) { bv = m; bp = pbase; }
             } else {
+              float k[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) bv = fmaxf(bv, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) k[i] = __uint_as_float(v[i]);
+              bv = fmaxf(bv, max32(k));
             }
-          }
-          best[chunk] = bv;
-          besti[chunk] = bi;
-          tc_fence_before();
-          named_bar_sync(2, 128);
-          if (tid == 128) mbar_arrive_cluster(bar(BAR_ACC3_EMPTY0 + buf), 0);
-          if (tid == 128) TSTAMP(10 + 3 * s);
+          };
+          const uint32_t t0 = lane_taddr + acc3_col(s);
+          uint32_t va[32], vb[32];
+          tmem_ld32(t0, va);
+          tmem_ld_wait();
+          tmem_ld32(t0 + 32, vb); e3_chunk(va, 0); tmem_ld_wait();
+          tmem_ld32(t0 + 64, va); e3_chunk(vb, 1); tmem_ld_wait();
+          tmem_ld32(t0 + 96, vb); e3_chunk(va, 2); tmem_ld_wait();
+          e3_chunk(vb, 3);
         }
+        best[chunk] = bv;
+        bestp[chunk] = bp;
+        tc_fence_before();
+        named_bar_sync(2, 128);
+        if (tid == 128) mbar_arrive_cluster(bar(BAR_ACC3_EMPTY0 + acc3_bar(s)), 0);
+        if (tid == 128) TSTAMP(10 + 3 * s);
       }
-      if (ok) {
+      if (!ok) break;
+      if (j == tpc - 1) {                                     // cloud complete: pooled outputs (bias after the pool)
 #pragma unroll
         for (int chunk = 0; chunk < 2; ++chunk) {
           const int ch = rank * 256 + chunk * 128 + lrow;
-          feat[(int64_t)b * ldf + ch] = best[chunk] + __ldg(b3 + ch);
-          if (WANT_ARGMAX) argmax[(int64_t)b * 512 + ch] = besti[chunk];
+          const uint32_t kb = __float_as_uint(best[chunk]);
+          if (WANT_ARGMAX) {
+            feat[(int64_t)b * ldf + ch] = __uint_as_float(kb & 0xFFFFFFE0u) + __ldg(b3 + ch);
+            argmax[(int64_t)b * 512 + ch] = bestp[chunk] + 31 - (int)(kb & 31u);
+          } else {
+            feat[(int64_t)b * ldf + ch] = best[chunk] + __ldg(b3 + ch);
+          }
+          best[chunk] = -INFINITY;
+          bestp[chunk] = 0;
         }
       }
     }
   } else if (rank == 0) {
     // =========================================================== warp 8 of the leader CTA: MMA issue
     const uint32_t idesc_l2 = umma_idesc(256, 256), idesc_l3 = umma_idesc(256, 128);
-    uint32_t it = 0;
-    for (int b = cluster_id; b < B && ok; b += n_clusters) {
-      for (int j = 0; j < tiles_per_cloud && ok; ++j, ++it) {
-        if (lane == 0) TSTAMP(24);
-        ok = mbar_wait(bar(BAR_H1_FULL), it & 1, err, 104);
+    auto l3_mma_acc = [&](int s, int k, bool acc) {           // one K=16 step of layer-3 group s (chunk s>>1, point half s&1)
+      const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
+      umma_bf16_2cta(tmem_base + acc3_col(s), umma_desc(sbase + SM_W3 + (s >> 1) * 65536 + koff),
+                     umma_desc(sbase + SM_H + (s & 1) * (64 * 128) + koff), idesc_l3, acc ? 1u : 0u);
+    };
+    auto l3_mma = [&](int s, int k) { l3_mma_acc(s, k, k > 0); };
+    for (int it = 0; it < n_tiles && ok; ++it) {
+      if (lane == 0) TSTAMP(24);
+      ok = mbar_wait(bar(BAR_H1_FULL), it & 1, err, 104) &&
+           mbar_wait(bar(BAR_ACC3_EMPTY2), (it & 1) ^ 1, err, 108);     // group 2 of the previous tile drained acc2's low half
+      if (!ok) break;
+      tc_fence_after();
+      if (lane == 0) TSTAMP(25);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                         // K = 128 = 2 k-blocks x 4 x UMMA_K(16)
+          const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
+          umma_bf16_2cta(tmem_base, umma_desc(sbase + SM_H + koff), umma_desc(sbase + SM_W2 + koff), idesc_l2, k > 0);
+        }
+        umma_commit_mc(bar(BAR_ACC2_FULL));
+      }
+      __syncwarp();
+      if (lane == 0) TSTAMP(26);
+      // ---- first channel chunk (groups 0,1): both TMEM buffers must be drained, then follow E2 k-block by k-block
+      ok = mbar_wait(bar(BAR_ACC3_EMPTY0), 1u, err, 106) && mbar_wait(bar(BAR_ACC3_EMPTY1), (it & 1) ^ 1, err, 106);
+      if (!ok) break;
+#pragma unroll 1
+      for (int q = 0; q < 4 && ok; ++q) {
+        const int kb = ((q & 1) << 1) | (q >> 1);              // readiness order: k-blocks 0, 2 (first halves of A / B), then 1, 3
+        ok = mbar_wait(bar(BAR_H2_KB0 + kb), it & 1, err, 105);
         if (!ok) break;
         tc_fence_after();
-        if (lane == 0) TSTAMP(25);
+        if (lane == 0) TSTAMP(27 + q);
         if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {                       // K = 128 = 2 k-blocks x 4 x UMMA_K(16)
-            const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
-            umma_bf16_2cta(tmem_base, umma_desc(sbase + SM_H + koff), umma_desc(sbase + SM_W2 + koff), idesc_l2, k > 0);
-          }
-          umma_commit_mc(bar(BAR_ACC2_FULL));
+          for (int k = 0; k < 4; ++k) l3_mma_acc(0, kb * 4 + k, q > 0 || k > 0);
+          if (q == 3) umma_commit_mc(bar(BAR_ACC3_FULL0));
+          for (int k = 0; k < 4; ++k) l3_mma_acc(1, kb * 4 + k, q > 0 || k > 0);
+          if (q == 3) umma_commit_mc(bar(BAR_ACC3_FULL1));
         }
         __syncwarp();
-        if (lane == 0) TSTAMP(26);
-        ok = mbar_wait(bar(BAR_H2_FULL), it & 1, err, 105);
-        if (!ok) break;
-        tc_fence_after();
-        if (lane == 0) TSTAMP(27);
-#pragma unroll 1
-        for (int s = 0; s < 4 && ok; ++s) {
-          const int buf = s & 1, chunk = s >> 1, half = s & 1;
-          ok = mbar_wait(bar(BAR_ACC3_EMPTY0 + buf), ((it * 2 + chunk) & 1) ^ 1, err, 106);
-          if (!ok) break;
-          tc_fence_after();
-          if (lane == 0) TSTAMP(28 + 2 * s);
-          if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {                    // K = 256 = 4 k-blocks x 4 x UMMA_K
-              const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
-              umma_bf16_2cta(tmem_base + 256 + buf * 128, umma_desc(sbase + SM_W3 + chunk * 65536 + koff),
-                             umma_desc(sbase + SM_H + half * (64 * 128) + koff), idesc_l3, k > 0);
-            }
-            umma_commit_mc(bar(BAR_ACC3_FULL0 + buf));
-            if (s == 3) umma_commit_mc(bar(BAR_L3_DONE));
-          }
-          __syncwarp();
-          if (lane == 0) TSTAMP(29 + 2 * s);
-        }
       }
+      if (!ok) break;
+      // ---- second channel chunk: group 2 goes straight into acc2's low half (E2 is done with it: H2_KB3 arrived),
+      //      group 3 into buffer 0 as soon as E3 has drained group 0
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) l3_mma(2, k);
+        umma_commit_mc(bar(BAR_ACC3_FULL2));
+      }
+      __syncwarp();
+      if (lane == 0) TSTAMP(32);
+      ok = mbar_wait(bar(BAR_ACC3_EMPTY0), 0u, err, 106);
+      if (!ok) break;
+      tc_fence_after();
+      if (lane == 0) TSTAMP(33);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) l3_mma(3, k);
+        umma_commit_mc(bar(BAR_ACC3_FULL0));
+        umma_commit_mc(bar(BAR_L3_DONE));
+      }
+      __syncwarp();
+      if (lane == 0) TSTAMP(34);
     }
   }
 
@@ -316,6 +432,7 @@ int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int
   PM_REQUIRE(N % PTS_PER_TILE == 0, PM_ERR_UNSUPPORTED, "bf16 encoder: N=%d must be a multiple of %d (use PM_PREC_FP32)", N, PTS_PER_TILE);
   PM_REQUIRE(ws && ws_bytes >= pm_pointnet_encode_forward_tc_ws_bytes(B, N, C), PM_ERR_ARG, "bf16 encoder: workspace too small");
   PM_REQUIRE(pm_aligned(ws, 256), PM_ERR_ALIGN, "bf16 encoder: workspace must be 256-byte aligned");
+  PM_REQUIRE(pm_aligned(p->b2, 16), PM_ERR_ALIGN, "bf16 encoder: b2 must be 16-byte aligned");
   cudaStream_t st = pm_st(s);
   uint8_t* wpack = reinterpret_cast<uint8_t*>(ws);
   int32_t* err = reinterpret_cast<int32_t*>(wpack + 2 * WPACK_PER_RANK);

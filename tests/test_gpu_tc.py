@@ -42,10 +42,12 @@ def test_tc_encoder_features_and_argmax(B, N, C, act):
     assert int(am.min()) >= 0 and int(am.max()) < N
     picked = h.gather(1, am[:, None, :]).squeeze(1)          # fp32 value at the point the bf16 kernel chose
     assert float((picked - want).abs().max()) <= 2e-2
-    # without argmax (rollout variant) the features are identical
+    # without argmax (rollout variant) the features agree up to the 5 mantissa bits the argmax variant borrows for the
+    # column index inside its max-pool key (2^-18 relative)
     feat2 = torch.empty(B, 512, device=DEV)
     ops.pointnet_encode_forward(cu(x), N, C, enc, act, "bf16", feat2, None, None, None)
-    assert ops.pointnet_tc_last_error(DEV) == 0 and torch.equal(feat, feat2)
+    assert ops.pointnet_tc_last_error(DEV) == 0
+    assert float((feat - feat2).abs().max()) <= 1e-5 * float(feat2.abs().max()) + 1e-7
 
 
 def test_tc_pointnet_golden_outputs_and_training_step():
