@@ -7,9 +7,8 @@ running stats; `count` is then the global env count.
 from __future__ import annotations
 
 import torch
-import torch.distributed as dist
 
-from ... import ops
+from ... import ops, parallel
 
 
 class RunningMeanStd:
@@ -24,14 +23,11 @@ class RunningMeanStd:
     def update(self, x):
         """RMS.py:10-18."""
         self.n += 1
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        count = float(x.shape[0] * world)
+        count = parallel.global_count(x.shape[0])
         ops.rms_colsum(x, self._colsum)
-        if world > 1:
-            dist.all_reduce(self._colsum)
+        parallel.all_reduce_sum_(self._colsum)
         ops.rms_colsqdev(x, self._colsum, count, self._sqdev)
-        if world > 1:
-            dist.all_reduce(self._sqdev)
+        parallel.all_reduce_sum_(self._sqdev)
         ops.rms_update(self.mean, self.S, self.std, self._colsum, self._sqdev, count, self.n)
 
     def load(self, load_dict):

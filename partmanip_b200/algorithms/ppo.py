@@ -21,14 +21,9 @@ from os.path import join as pjoin
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
-from .. import ops
+from .. import ops, parallel
 from .algo_utils import ActorCritic, Normalization, RolloutStorage
-
-
-def _world():
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 class FlatAdam:
@@ -141,12 +136,11 @@ class ppo:
             self.state_norm = Normalization(shape=self.num_obs, device=self.device)
             self.update_RMS = True
         # network, buffer, optimisers (ppo.py:70-74)
-        self.world = _world()
+        self.world = parallel.world()
         self.actor_critic = ActorCritic(self.num_obs, self.num_actions, self.model_cfg).to(self.device)
         ac = self.actor_critic.flatten_()
-        if self.world > 1:   # identical replicas
-            dist.broadcast(ac.actor_flat, 0)
-            dist.broadcast(ac.critic_flat, 0)
+        parallel.broadcast_(ac.actor_flat)      # identical replicas
+        parallel.broadcast_(ac.critic_flat)
         self.storage = RolloutStorage(self.num_envs, self.n_steps, self.num_obs, self.num_actions, self.device,
                                       self.default_succ_value, self.tricks['whole_adv_norm'], cfg['sampler'])
         a_params = list(ac.actor.parameters())
@@ -380,12 +374,10 @@ class ppo:
                 ops.ppo_actor_loss(mu, ac.log_std.data, mb['act'], mb['logp'].reshape(-1), mb['mu'], mb['sigma'],
                                    mb['adv'].reshape(-1), adv_stats, inv_b, self.epsilon_clip, ac.max_action, squash,
                                    self._stats_a, dmu, self._actor_grads[-1])
-                if world > 1:
-                    dist.all_reduce(self._stats_a)      # rank-consistent KL-skip decision
+                parallel.all_reduce_sum_(self._stats_a)      # rank-consistent KL-skip decision
                 ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)
                 ac.actor.runner.backward(mb['obs'], dmu, self._actor_grads[:-1])
-                if world > 1:
-                    dist.all_reduce(self.optimizer_actor.grad)
+                parallel.all_reduce_sum_(self.optimizer_actor.grad)
                 self.optimizer_actor.step(self._skip)
         # ---- phase 2: critic (ppo.py:359-384)
         n_critic = 0
@@ -400,19 +392,16 @@ class ppo:
                 clip_delta = None
                 if self.tricks['use_clipped_value_loss']:
                     ops.abs_sum(mb['val'].reshape(-1), self.epsilon_clip * inv_b, self._clip_delta)
-                    if world > 1:
-                        dist.all_reduce(self._clip_delta)
+                    parallel.all_reduce_sum_(self._clip_delta)
                     clip_delta = self._clip_delta
                 ops.value_loss(v, mb['ret'].reshape(-1), mb['val'].reshape(-1), clip_delta, inv_b, self._stats_v, dv)
                 ops.accumulate(self._stats_v, inv_b, self._acc, 4)
                 ac.critic.runner.backward(mb['obs'], dv, self._critic_grads)
-                if world > 1:
-                    dist.all_reduce(self.optimizer_critic.grad)
+                parallel.all_reduce_sum_(self.optimizer_critic.grad)
                 self.optimizer_critic.step(None)
                 n_critic += 1
         # ---- one read-back per iteration
-        if world > 1:
-            dist.all_reduce(self._acc[4:5])
+        parallel.all_reduce_sum_(self._acc[4:5])
         acc = self._acc.tolist()
         count = int(round(acc[2]))
         mean_value_loss = acc[4] / max(n_critic, 1)

@@ -17,7 +17,7 @@ class FakeVecEnv:
     def __init__(self, num_envs: int, obs_dim: int, num_actions: int, device, *, obs_mode: str = "obs",
                  cloud: bool = True, channels: int = 3, pool: int = 16, seed: int = 1234, succ_p: float = 0.0,
                  done_p: float = 0.05, host: bool = False, extra_obs: Optional[Dict[str, int]] = None,
-                 max_episode_length: int = 200):
+                 max_episode_length: int = 200, shard=None):
         self.num_envs, self.num_actions, self.max_episode_length = num_envs, num_actions, max_episode_length
         self.device = torch.device(device)
         self.obs_mode = obs_mode
@@ -27,7 +27,10 @@ class FakeVecEnv:
         self.train_test_flag = "train"
         self.host = host
         g = torch.Generator().manual_seed(seed)
-        E, D = num_envs, obs_dim
+        # shard=(rank, world): generate the GLOBAL env batch of num_envs*world envs and keep this rank's slice, so that
+        # R ranks see exactly the data one process with R*num_envs envs sees (multi-GPU parity runs)
+        srank, sworld = shard if shard is not None else (0, 1)
+        E, D = num_envs * sworld, obs_dim
 
         def make_obs():
             if cloud:
@@ -49,6 +52,12 @@ class FakeVecEnv:
         self._rew = [torch.randn(E, generator=g) for _ in range(pool)]
         self._done = [torch.rand(E, generator=g) < done_p for _ in range(pool)]
         self._succ = [torch.rand(E, generator=g) < succ_p for _ in range(pool)]
+        if sworld > 1:
+            cut = lambda t: t[srank * num_envs:(srank + 1) * num_envs].contiguous()
+            self._pool = [cut(t) for t in self._pool]
+            self._extra_pool = {k: [cut(t) for t in v] for k, v in self._extra_pool.items()}
+            self._rew, self._done, self._succ = [cut(t) for t in self._rew], [cut(t) for t in self._done], [cut(t) for t in self._succ]
+        E = num_envs
         if host:
             self._pool = [t.pin_memory() for t in self._pool]
             self._obs_dev = torch.empty(E, D, device=self.device)
