@@ -399,9 +399,45 @@ __global__ void reduce_slabs_kernel(const float* __restrict__ part, int slabs, i
   out[i] = t;
 }
 
+// mean-pool branch (max_mean=True, network.py:180-182): every point receives dfeat_mean[b,c]/N through layer 3
+// gm[b,k] = (1/N) sum_c dfeat_mean[b,c] W3[c,k]   — the part of dH2 that is common to all points of cloud b
+__global__ void __launch_bounds__(256)
+mean_gm_kernel(const float* __restrict__ dfm, int64_t lddf, const float* __restrict__ W3, float inv_n, float* __restrict__ gm) {
+  __shared__ float sd[512];
+  const int b = blockIdx.x, k = threadIdx.x;
+  for (int c = k; c < 512; c += 256) sd[c] = dfm[(int64_t)b * lddf + c];
+  __syncthreads();
+  float a = 0.f;
+  for (int c = 0; c < 512; ++c) a = fmaf(sd[c], __ldg(W3 + (int64_t)c * 256 + k), a);
+  gm[(int64_t)b * 256 + k] = a * inv_n;
+}
+// dW3[c,k] += sum_b dfeat_mean[b,c] h2mean[b,k] ; db3[c] += sum_b dfeat_mean[b,c]   (mean_n h3 = W3 mean_n h2 + b3)
+__global__ void __launch_bounds__(256)
+mean_dw3_kernel(const float* __restrict__ dfm, int64_t lddf, const float* __restrict__ h2mean, int B, float* __restrict__ dW3,
+                float* __restrict__ db3) {
+  const int k = threadIdx.x, c0 = blockIdx.x * DW3_CH;
+  float acc[DW3_CH], dbs[DW3_CH];
+#pragma unroll
+  for (int j = 0; j < DW3_CH; ++j) { acc[j] = 0.f; dbs[j] = 0.f; }
+  for (int b = 0; b < B; ++b) {
+    const float h = h2mean[(int64_t)b * 256 + k];
+#pragma unroll
+    for (int j = 0; j < DW3_CH; ++j) {
+      const float g = dfm[(int64_t)b * lddf + c0 + j];
+      acc[j] = fmaf(g, h, acc[j]);
+      dbs[j] += g;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DW3_CH; ++j) {
+    dW3[(int64_t)(c0 + j) * 256 + k] += acc[j];
+    if (k == 0) db3[c0 + j] += dbs[j];
+  }
+}
+
 struct BwdWs {
   int32_t *ucount, *rowoff, *r_dev, *row_b, *row_cbeg, *row_ccnt, *chan_sorted, *slot;
-  float *Xc, *H1c, *H2c, *dPre2, *dPre1, *dw3part, *db3part, *lin;
+  float *Xc, *H1c, *H2c, *dPre2, *dPre1, *dw3part, *db3part, *gm, *lin;
   size_t lin_bytes, total;
   int slabs, b_per_slab;
   int64_t rmax;
@@ -431,6 +467,7 @@ inline BwdWs carve_bwd(void* ws, int B, int N, int C, int with_mean) {
   w.dPre1 = (float*)take((size_t)rmax * 128 * 4);
   w.dw3part = (float*)take((size_t)w.slabs * 512 * 256 * 4);
   w.db3part = (float*)take((size_t)w.slabs * 512 * 4);
+  w.gm = (float*)take(with_mean ? (size_t)B * 256 * 4 : 0);
   size_t l1 = pm_linear_backward_ws_bytes((int)(rmax > INT32_MAX ? INT32_MAX : rmax), 256, 128);
   size_t l2 = pm_linear_backward_ws_bytes((int)(rmax > INT32_MAX ? INT32_MAX : rmax), 128, C);
   w.lin_bytes = l1 > l2 ? l1 : l2;
@@ -496,8 +533,7 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
     return pm_pointnet_encode_backward_tc(x, ldx, B, N, C, p, act, dfeat, lddf, argmax, g, ws, ws_bytes, s);
   }
   PM_REQUIRE(precision == PM_PREC_FP32, PM_ERR_ARG, "pm_pointnet_encode_backward: precision %d", precision);
-  PM_REQUIRE(!dfeat_mean, PM_ERR_UNSUPPORTED, "pm_pointnet_encode_backward: mean-pool branch (max_mean=True) backward not built yet");
-  (void)h2mean;
+  PM_REQUIRE(!dfeat_mean || h2mean, PM_ERR_ARG, "pm_pointnet_encode_backward: the mean-pool branch needs h2mean from the forward");
   const int with_mean = dfeat_mean != nullptr;
   BwdWs w = carve_bwd(ws, B, N, C, with_mean);
   PM_REQUIRE(ws_bytes >= w.total, PM_ERR_ARG, "pm_pointnet_encode_backward: workspace %zu < %zu", ws_bytes, w.total);
@@ -515,12 +551,14 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
   crit_layer1_kernel<<<grid_rows, 128, 0, st>>>(w.Xc, C, p->W1, p->b1, act, w.r_dev, w.H1c);
   if ((rc = pm_linear_forward(w.H1c, 128, p->W2, p->b2, w.H2c, 256, rmax, 256, 128, act, w.r_dev, s))) return rc;
   // 3. layer 3: dPre2 rows and dW3/db3
+  if (with_mean) mean_gm_kernel<<<B, 256, 0, st>>>(dfeat_mean, lddf, p->W3, 1.f / (float)N, w.gm);
   crit_dh2_kernel<<<grid_rows, 256, 0, st>>>(dfeat, lddf, p->W3, w.H2c, w.row_b, w.row_cbeg, w.row_ccnt, w.chan_sorted,
-                                              nullptr, act, w.r_dev, w.dPre2);
+                                              with_mean ? w.gm : nullptr, act, w.r_dev, w.dPre2);
   crit_dw3_kernel<<<dim3(512 / DW3_CH, w.slabs), 256, 0, st>>>(dfeat, lddf, w.H2c, w.slot, B, w.b_per_slab, w.dw3part,
                                                                 w.db3part);
   reduce_slabs_kernel<<<pm_cdiv(512 * 256, 256), 256, 0, st>>>(w.dw3part, w.slabs, 512 * 256, g->W3);
   reduce_slabs_kernel<<<2, 256, 0, st>>>(w.db3part, w.slabs, 512, g->b3);
+  if (with_mean) mean_dw3_kernel<<<512 / DW3_CH, 256, 0, st>>>(dfeat_mean, lddf, h2mean, B, g->W3, g->b3);
   PM_CHECK_LAUNCH("pm_pointnet_encode_backward/crit");
   // 4. layer 2: dW2, db2, dPre1 = (dPre2 W2) * act'(H1c)
   if ((rc = pm_linear_backward(w.H1c, 128, p->W2, w.dPre2, 256, g->W2, g->b2, w.dPre1, 128, rmax, 256, 128, act,

@@ -49,7 +49,7 @@ def test_pointnet_golden_forward(name):
         assert not torch.equal(x.cpu(), g["x"])
 
 
-@pytest.mark.parametrize("name", [n for n in PN_CASES if not PN_CASES[n]["cfg"]["max_mean"]])
+@pytest.mark.parametrize("name", list(PN_CASES))
 def test_pointnet_golden_backward(name):
     g, net = _build(name)
     y = net(cu(g["x"]))
