@@ -88,6 +88,12 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
                const float* __restrict__ dfeat, int64_t lddf, const uint8_t* __restrict__ w2img,
                const uint32_t* __restrict__ w3pack, const float* __restrict__ W1, const float* __restrict__ b1,
                const float* __restrict__ b2, float* __restrict__ part_all, int32_t* __restrict__ err) {
+#ifdef PM_TC_TIMING
+  long long* dbg = reinterpret_cast<long long*>(err + 16);
+#define BSTAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && it == 3) dbg[(slot)] = clock64(); } while (0)
+#else
+#define BSTAMP(slot) do { } while (0)
+#endif
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -174,6 +180,7 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       const float g = g_nxt;
       const float xv[4] = {xn0, xn1, xn2, xn3};
       if (it + 1 < n_tiles) load_row(slab + (it + 1) * n_slabs, g_nxt, xn0, xn1, xn2, xn3);   // prefetch the next tile's row
+      BSTAMP(0);
       // ---- S1: layer 1 for this thread's 64 channels (= one k-block of H1)
       {
         uint32_t h1[32];
@@ -192,7 +199,9 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         if (hsel == 0) { sXs[r] = make_float4(xv[0], xv[1], xv[2], xv[3]); db3 += g; }
       }
       fence_proxy_async();
+      BSTAMP(1);
       __syncthreads();
+      BSTAMP(2);
       if (tid == 0) {                                              // M1: D2 = H1 . W2^T, K = 128 h1 channels
         tc_fence_after();
 #pragma unroll
@@ -205,9 +214,11 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       }
       __syncwarp();
       // ---- S2: H2, dW3 accumulation, dPre2
+      BSTAMP(3);
       ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 201);
       if (!ok) break;
       tc_fence_after();
+      BSTAMP(4);
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = hsel * 128 + cc * 32;
@@ -234,7 +245,9 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       }
       tc_fence_before();
       fence_proxy_async();
+      BSTAMP(5);
       __syncthreads();
+      BSTAMP(6);
       if (tid == 0) {
         tc_fence_after();
 #pragma unroll
@@ -253,6 +266,7 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         umma_commit_1cta(bar(BAR_ACC1_FULL));
       }
       __syncwarp();
+      BSTAMP(7);
       // ---- db2 column sums over the tile (thread tid owns h2 channel tid) while the MMAs run
       {
         const uint32_t base = SB_DP2 + (tid >> 6) * KB16 + (tid & 7) * 2;
@@ -268,10 +282,12 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         }
         db2 += s;
       }
+      BSTAMP(8);
       // ---- S3: dPre1 = dH1 * act'(H1), in place over H1
       ok = mbar_wait(bar(BAR_ACC1_FULL), it & 1, err, 202);
       if (!ok) break;
       tc_fence_after();
+      BSTAMP(9);
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -293,7 +309,9 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         }
       }
       tc_fence_before();
+      BSTAMP(10);
       __syncthreads();
+      BSTAMP(11);
       // ---- dW1 / db1 column sums (thread owns h1 channel tid&127 over row half tid>>7)
       {
         const int jc = tid & 127, half = tid >> 7;
@@ -313,7 +331,9 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
           }
         }
       }
+      BSTAMP(12);
       __syncthreads();                                             // H1 / Xs / dPre2 free for the next tile
+      BSTAMP(13);
     }
 
     // ---------------- epilogue: partial gradients of this CTA

@@ -35,12 +35,14 @@ constexpr uint32_t SM_BAR = 231936;      // 13 mbarriers (104 B) + tmem base (4 
 constexpr uint32_t SM_TOTAL = 232064;
 constexpr uint32_t KBLOCK_BYTES = 128 * 128;   // one 64-wide k-block of a 128-row operand
 
-enum { BAR_H1_FULL = 0, BAR_ACC2_FULL, BAR_H2_KB0, BAR_H2_KB1, BAR_H2_KB2, BAR_H2_KB3, BAR_ACC3_FULL0, BAR_ACC3_FULL1,
-       BAR_ACC3_FULL2, BAR_ACC3_EMPTY0, BAR_ACC3_EMPTY1, BAR_ACC3_EMPTY2, BAR_L3_DONE, NUM_BARS };
-// layer-3 accumulator of MMA group s (TMEM column base): groups 0/3 -> buffer 0 [256,384), group 1 -> buffer 1 [384,512),
-// group 2 -> the low half of the layer-2 accumulator [0,128), which is free once E2 has read it
-__host__ __device__ constexpr uint32_t acc3_col(int s) { return s == 2 ? 0u : (s == 1 ? 384u : 256u); }
-__host__ __device__ constexpr int acc3_bar(int s) { return s == 2 ? 2 : (s == 1 ? 1 : 0); }
+enum { BAR_H1_FULL = 0, BAR_ACC2_FULL, BAR_H2_KB0, BAR_H2_KB1, BAR_H2_KB2, BAR_H2_KB3, BAR_G_FULL0, BAR_G_FULL1,
+       BAR_G_EMPTY0, BAR_G_EMPTY1, BAR_L3_DONE, NUM_BARS };
+// TMEM plan: two 256-column regions that swap roles every tile (p = tile parity):
+//   region p   : layer-2 accumulator of this tile, then (once E2 has read it) layer-3 group 1 (channel chunk 1)
+//   region p^1 : layer-3 group 0 (channel chunk 0) of this tile; it held group 1 of the previous tile
+// Both layer-3 groups are N=256 MMAs (all 256 points of the pair tile): half the shared-memory operand traffic per
+// flop of the N=128 shape, which ran at ~70 % of the tensor rate because the W3 operand stream saturated SMEM.
+__host__ __device__ constexpr uint32_t region_col(int p) { return p ? 256u : 0u; }
 
 // packed weight image per network, per CTA rank: [W3 half (131072) | W2 half (32768)] ready to memcpy into smem
 constexpr size_t WPACK_PER_RANK = 131072 + 32768;
@@ -161,7 +163,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     mbar_init(bar(BAR_H1_FULL), 2);
     mbar_init(bar(BAR_ACC2_FULL), 1);
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar(BAR_H2_KB0 + kb), 2);
-    for (int i = 0; i < 3; ++i) { mbar_init(bar(BAR_ACC3_FULL0 + i), 1); mbar_init(bar(BAR_ACC3_EMPTY0 + i), 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_G_FULL0 + i), 1); mbar_init(bar(BAR_G_EMPTY0 + i), 2); }
     mbar_init(bar(BAR_L3_DONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -253,7 +255,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       if (!ok) break;
       tc_fence_after();
       if (tid == 0) TSTAMP(4);
-      e2_half(lane_taddr, row, 0, ba0, 1, 0);
+      e2_half(lane_taddr + region_col(it & 1), row, 0, ba0, 1, 0);
       if (tid == 0) TSTAMP(5);
     }
   } else if (warp < 8) {
@@ -273,20 +275,18 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 109);
         if (!ok) break;
         tc_fence_after();
-        e2_half(lane_taddr, lrow, 4, bb0, 2, 128);
+        e2_half(lane_taddr + region_col(it & 1), lrow, 4, bb0, 2, 128);
         if (tid == 128) TSTAMP(21);
       }
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int chunk = s >> 1, half = s & 1;
-        if (tid == 128) TSTAMP(8 + 3 * s);
-        // buffer 0 completes two phases per tile (groups 0 and 3), buffers 1 and 2 one each
-        ok = mbar_wait(bar(BAR_ACC3_FULL0 + acc3_bar(s)), s == 0 ? 0u : (s == 3 ? 1u : (uint32_t)(it & 1)), err, 103);
+      for (int g = 0; g < 2; ++g) {                           // layer-3 group g = channel chunk g, all 256 points of the tile
+        if (tid == 128) TSTAMP(8 + 3 * g);
+        ok = mbar_wait(bar(BAR_G_FULL0 + g), it & 1, err, 103);
         if (!ok) break;
         tc_fence_after();
-        if (tid == 128) TSTAMP(9 + 3 * s);
-        float bv = best[chunk];
-        int bp = bestp[chunk];
+        if (tid == 128) TSTAMP(9 + 3 * g);
+        float bv = best[g];
+        int bp = bestp[g];
         {
           auto e3_chunk = [&](uint32_t (&v)[32], int cc) {      // 32 columns (points) of this thread's channel
             if (WANT_ARGMAX) {
@@ -296,8 +296,8 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
 #pragma unroll
               for (int i = 0; i < 32; ++i) k[i] = __uint_as_float((v[i] & 0xFFFFFFE0u) | (uint32_t)(31 - i));
               const float m = max32(k);
-              // column n -> point: columns [0,64) come from CTA 0's rows, [64,128) from CTA 1's (B operand N halves)
-              const int pbase = j * PTS_PER_TILE + (cc >> 1) * PTS_PER_CTA + half * 64 + (cc & 1) * 32;
+              // column n -> point: columns [0,128) are CTA 0's rows, [128,256) CTA 1's (the B operand's N halves)
+              const int pbase = j * PTS_PER_TILE + cc * 32;
               if (m > bv) { bv = m; bp = pbase; }
             } else {
               float k[32];
@@ -306,21 +306,24 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
               bv = fmaxf(bv, max32(k));
             }
           };
-          const uint32_t t0 = lane_taddr + acc3_col(s);
+          const uint32_t t0 = lane_taddr + region_col((it & 1) ^ (g ^ 1));     // group 0: region p^1, group 1: region p
           uint32_t va[32], vb[32];
           tmem_ld32(t0, va);
           tmem_ld_wait();
-          tmem_ld32(t0 + 32, vb); e3_chunk(va, 0); tmem_ld_wait();
-          tmem_ld32(t0 + 64, va); e3_chunk(vb, 1); tmem_ld_wait();
-          tmem_ld32(t0 + 96, vb); e3_chunk(va, 2); tmem_ld_wait();
-          e3_chunk(vb, 3);
+#pragma unroll
+          for (int c2 = 0; c2 < 4; ++c2) {
+            tmem_ld32(t0 + (2 * c2 + 1) * 32, vb); e3_chunk(va, 2 * c2); tmem_ld_wait();
+            if (c2 < 3) tmem_ld32(t0 + (2 * c2 + 2) * 32, va);
+            e3_chunk(vb, 2 * c2 + 1);
+            if (c2 < 3) tmem_ld_wait();
+          }
         }
-        best[chunk] = bv;
-        bestp[chunk] = bp;
+        best[g] = bv;
+        bestp[g] = bp;
         tc_fence_before();
         named_bar_sync(2, 128);
-        if (tid == 128) mbar_arrive_cluster(bar(BAR_ACC3_EMPTY0 + acc3_bar(s)), 0);
-        if (tid == 128) TSTAMP(10 + 3 * s);
+        if (tid == 128) mbar_arrive_cluster(bar(BAR_G_EMPTY0 + g), 0);
+        if (tid == 128) TSTAMP(10 + 3 * g);
       }
       if (!ok) break;
       if (j == tpc - 1) {                                     // cloud complete: pooled outputs (bias after the pool)
@@ -341,17 +344,17 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     }
   } else if (rank == 0) {
     // =========================================================== warp 8 of the leader CTA: MMA issue
-    const uint32_t idesc_l2 = umma_idesc(256, 256), idesc_l3 = umma_idesc(256, 128);
-    auto l3_mma_acc = [&](int s, int k, bool acc) {           // one K=16 step of layer-3 group s (chunk s>>1, point half s&1)
+    const uint32_t idesc = umma_idesc(256, 256);             // every MMA of this kernel: M=256 (pair), N=256, K=16
+    auto l3_mma = [&](int chunk, uint32_t dcol, int k, bool acc) {   // one K=16 step of layer-3 channel chunk `chunk`
       const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
-      umma_bf16_2cta(tmem_base + acc3_col(s), umma_desc(sbase + SM_W3 + (s >> 1) * 65536 + koff),
-                     umma_desc(sbase + SM_H + (s & 1) * (64 * 128) + koff), idesc_l3, acc ? 1u : 0u);
+      umma_bf16_2cta(tmem_base + dcol, umma_desc(sbase + SM_W3 + chunk * 65536 + koff), umma_desc(sbase + SM_H + koff), idesc,
+                     acc ? 1u : 0u);
     };
-    auto l3_mma = [&](int s, int k) { l3_mma_acc(s, k, k > 0); };
     for (int it = 0; it < n_tiles && ok; ++it) {
+      const uint32_t colp = region_col(it & 1), colq = region_col((it & 1) ^ 1);
       if (lane == 0) TSTAMP(24);
-      ok = mbar_wait(bar(BAR_H1_FULL), it & 1, err, 104) &&
-           mbar_wait(bar(BAR_ACC3_EMPTY2), (it & 1) ^ 1, err, 108);     // group 2 of the previous tile drained acc2's low half
+      // region p held layer-3 group 0 of the previous tile: E3 must have drained it before layer 2 overwrites it
+      ok = mbar_wait(bar(BAR_H1_FULL), it & 1, err, 104) && mbar_wait(bar(BAR_G_EMPTY0), (it & 1) ^ 1, err, 108);
       if (!ok) break;
       tc_fence_after();
       if (lane == 0) TSTAMP(25);
@@ -359,14 +362,14 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                         // K = 128 = 2 k-blocks x 4 x UMMA_K(16)
           const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
-          umma_bf16_2cta(tmem_base, umma_desc(sbase + SM_H + koff), umma_desc(sbase + SM_W2 + koff), idesc_l2, k > 0);
+          umma_bf16_2cta(tmem_base + colp, umma_desc(sbase + SM_H + koff), umma_desc(sbase + SM_W2 + koff), idesc, k > 0);
         }
         umma_commit_mc(bar(BAR_ACC2_FULL));
       }
       __syncwarp();
       if (lane == 0) TSTAMP(26);
-      // ---- first channel chunk (groups 0,1): both TMEM buffers must be drained, then follow E2 k-block by k-block
-      ok = mbar_wait(bar(BAR_ACC3_EMPTY0), 1u, err, 106) && mbar_wait(bar(BAR_ACC3_EMPTY1), (it & 1) ^ 1, err, 106);
+      // ---- group 0 (channel chunk 0) into region p^1 (held group 1 of the previous tile), k-block by k-block behind E2
+      ok = mbar_wait(bar(BAR_G_EMPTY1), (it & 1) ^ 1, err, 106);
       if (!ok) break;
 #pragma unroll 1
       for (int q = 0; q < 4 && ok; ++q) {
@@ -376,35 +379,21 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         tc_fence_after();
         if (lane == 0) TSTAMP(27 + q);
         if (lane == 0) {
-          for (int k = 0; k < 4; ++k) l3_mma_acc(0, kb * 4 + k, q > 0 || k > 0);
-          if (q == 3) umma_commit_mc(bar(BAR_ACC3_FULL0));
-          for (int k = 0; k < 4; ++k) l3_mma_acc(1, kb * 4 + k, q > 0 || k > 0);
-          if (q == 3) umma_commit_mc(bar(BAR_ACC3_FULL1));
+          for (int k = 0; k < 4; ++k) l3_mma(0, colq, kb * 4 + k, q > 0 || k > 0);
+          if (q == 3) umma_commit_mc(bar(BAR_G_FULL0));
         }
         __syncwarp();
       }
       if (!ok) break;
-      // ---- second channel chunk: group 2 goes straight into acc2's low half (E2 is done with it: H2_KB3 arrived),
-      //      group 3 into buffer 0 as soon as E3 has drained group 0
+      // ---- group 1 (channel chunk 1) into region p: E2 is done with the layer-2 accumulator (all four k-blocks arrived)
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) l3_mma(2, k);
-        umma_commit_mc(bar(BAR_ACC3_FULL2));
-      }
-      __syncwarp();
-      if (lane == 0) TSTAMP(32);
-      ok = mbar_wait(bar(BAR_ACC3_EMPTY0), 0u, err, 106);
-      if (!ok) break;
-      tc_fence_after();
-      if (lane == 0) TSTAMP(33);
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) l3_mma(3, k);
-        umma_commit_mc(bar(BAR_ACC3_FULL0));
+        for (int k = 0; k < 16; ++k) l3_mma(1, colp, k, k > 0);
+        umma_commit_mc(bar(BAR_G_FULL1));
         umma_commit_mc(bar(BAR_L3_DONE));
       }
       __syncwarp();
-      if (lane == 0) TSTAMP(34);
+      if (lane == 0) TSTAMP(32);
     }
   }
 

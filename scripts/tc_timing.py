@@ -24,10 +24,10 @@ for cta in range(2):
     base = int(t[0])
     lab = {0: "A tile start", 1: "A L1 done", 2: "A L3_DONE(prev) ok", 3: "A H1 stored+arrive", 4: "A ACC2_FULL ok", 5: "A E2 done",
            20: "B wait ACC2_FULL", 21: "B E2 half done", 24: "M wait H1", 25: "M H1_FULL ok", 26: "M L2 issued",
-           27: "M H2_KB0 ok", 28: "M H2_KB2 ok", 29: "M H2_KB1 ok", 30: "M H2_KB3 ok", 32: "M s2 issued",
-           33: "M s3 EMPTY ok", 34: "M s3 issued"}
-    for s in range(4):
-        lab[8 + 3 * s] = f"B s{s} wait"; lab[9 + 3 * s] = f"B s{s} ACC3_FULL ok"; lab[10 + 3 * s] = f"B s{s} done"
+           27: "M H2_KB0 ok", 28: "M H2_KB2 ok", 29: "M H2_KB1 ok", 30: "M H2_KB3 ok", }
+    for s in range(2):
+        lab[8 + 3 * s] = f"B g{s} wait"; lab[9 + 3 * s] = f"B g{s} FULL ok"; lab[10 + 3 * s] = f"B g{s} done"
+    lab[32] = "M g1 issued"
     print(f"--- CTA {cta}")
     for k in sorted(lab, key=lambda k: int(t[k])):
         if int(t[k]):
