@@ -21,7 +21,7 @@
 namespace {
 using namespace pmtc;
 
-constexpr int TC_THREADS = 288;          // warps 0-3: L1 + E2 | warps 4-7: E3 | warp 8: TMEM alloc + MMA issue
+constexpr int TC_THREADS = 544;          // warps 0-3 A0 | 4-7 A1 | 8-11 B0 | 12-15 B1 (epilogue groups, 4 per scheduler) | warp 16: TMEM alloc + MMA issue
 constexpr int PTS_PER_CTA = 128;
 constexpr int PTS_PER_TILE = 256;
 
@@ -90,6 +90,13 @@ __device__ __forceinline__ float max32(const float (&k)[32]) {
   return fmax3(m0, m1, fmaxf(m2, m3));
 }
 
+// max of 16 values: 8 FMNMX(3)
+__device__ __forceinline__ float max16(const float (&k)[16]) {
+  const float m0 = fmax3(k[0], k[1], k[2]), m1 = fmax3(k[3], k[4], k[5]), m2 = fmax3(k[6], k[7], k[8]);
+  const float m3 = fmax3(k[9], k[10], k[11]), m4 = fmax3(k[12], k[13], k[14]);
+  return fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, k[15]));
+}
+
 // layer 1 for the 16-byte chunks [C0, C1) of this thread's point row: h[(c-C0)*4 + q] = bf16x2 of channels 8c+2q, 8c+2q+1
 template <int ACT, int C0, int C1>
 __device__ __forceinline__ void layer1_part(const float (&xv)[4], const float* sW1, const float* sB1, uint32_t (&h)[(C1 - C0) * 4]) {
@@ -129,7 +136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, const uint8_t* __restrict__ wpack,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ b2,
                const float* __restrict__ b3, float* __restrict__ feat, int64_t ldf,
-               int32_t* __restrict__ argmax, int32_t* __restrict__ err) {
+               int32_t* __restrict__ argmax, int32_t* __restrict__ err, uint8_t* __restrict__ scratch) {
 #ifdef PM_TC_TIMING
   long long* dbg = reinterpret_cast<long long*>(err + 16);
 #define TSTAMP(slot) do { if (blockIdx.x < 2 && it == 3) dbg[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
@@ -160,14 +167,14 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     if (tid < 128) sB1[tid] = b1[tid];
   }
   if (tid == 0) {
-    mbar_init(bar(BAR_H1_FULL), 2);
+    mbar_init(bar(BAR_H1_FULL), 4);
     mbar_init(bar(BAR_ACC2_FULL), 1);
-    for (int kb = 0; kb < 4; ++kb) mbar_init(bar(BAR_H2_KB0 + kb), 2);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_G_FULL0 + i), 1); mbar_init(bar(BAR_G_EMPTY0 + i), 2); }
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar(BAR_H2_KB0 + kb), 8);    // 4 epilogue groups x 2 CTAs
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(BAR_G_FULL0 + i), 1); mbar_init(bar(BAR_G_EMPTY0 + i), 4); }
     mbar_init(bar(BAR_L3_DONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {   // one warp per CTA allocates all 512 TMEM columns for the pair
+  if (warp == 16) {   // one warp per CTA allocates all 512 TMEM columns for the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -179,56 +186,58 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   const uint32_t tmem_base = *tmem_slot;
   bool ok = true;
 
-  // ---- layer-2 epilogue of one 128-column half of acc2 (two 64-channel k-blocks of H2): acc2 row -> +b2 -> act -> bf16 ->
-  //      smem, with the tcgen05.ld and the b2 loads of chunk c+1 in flight while chunk c is processed (b2 comes from L2: the
-  //      227 KB carve-out leaves almost no L1).  Groups A and B each take one half, so two warps per scheduler interleave
-  //      their MUFU.TANH streams with the other's FADD / pack / store work.
-  auto e2_half = [&](uint32_t lane_taddr, int row, int cc0, const float4 (&b0)[8], int bar_id, int tid0) {
-    auto e2_chunk = [&](const uint32_t (&v)[32], const float4 (&bb)[8], int cc) {
-      uint32_t pk[16];
+  // ---- layer-2 epilogue: acc row -> +b2 -> act -> bf16 -> smem.  Each of the four epilogue groups takes the SAME 16-column
+  //      slice (slice = group index) of every 64-channel k-block of H2, so the k-blocks complete one after the other (not all
+  //      at the end) and the layer-3 MMAs of group 0 follow the epilogue k-block by k-block; four warps per scheduler
+  //      interleave their MUFU.TANH / FADD / pack / store streams.  The tcgen05.ld and the b2 loads (from L2: the 227 KB
+  //      carve-out leaves almost no L1) of k-block kb+1 are in flight while k-block kb is processed.
+  auto load_b2 = [&](float4 (&bb)[4], int col) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(b2 + col) + q);
+  };
+  auto e2_slices = [&](uint32_t taddr, int row, int sc, const float4 (&bfirst)[4], int bar_id, bool elect) {
+    auto e2_sub = [&](const uint32_t (&v)[16], const float4 (&bb)[4], int kb) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
         const float a0 = __uint_as_float(v[4 * q]) + bb[q].x, a1 = __uint_as_float(v[4 * q + 1]) + bb[q].y;
         const float a2 = __uint_as_float(v[4 * q + 2]) + bb[q].z, a3 = __uint_as_float(v[4 * q + 3]) + bb[q].w;
         pk[2 * q] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
         pk[2 * q + 1] = pack_bf16(act_fast<ACT>(a2), act_fast<ACT>(a3));
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t off = SM_H + (cc >> 1) * KBLOCK_BYTES + sw128(row, (cc & 1) * 4 + q);
-        *reinterpret_cast<uint4*>(smem + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      }
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(smem + SM_H + kb * KBLOCK_BYTES + sw128(row, 2 * sc + q)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     };
-    auto load_b2 = [&](float4 (&bb)[8], int cc) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(b2 + cc * 32) + q);
-    };
-    uint32_t va[32], vb[32];
-    float4 ba[8], bbv[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) ba[q] = b0[q];
-    tmem_ld32(lane_taddr + cc0 * 32, va);
-    tmem_ld_wait();
-#pragma unroll 1
-    for (int kk = 0; kk < 2; ++kk) {                           // k-block (cc0/2 + kk) of H2 = chunks cc0+2kk, cc0+2kk+1
-      const int cc = cc0 + 2 * kk;
-      tmem_ld32(lane_taddr + (cc + 1) * 32, vb);
-      load_b2(bbv, cc + 1);
-      e2_chunk(va, ba, cc);
-      tmem_ld_wait();
-      if (kk == 0) { tmem_ld32(lane_taddr + (cc + 2) * 32, va); load_b2(ba, cc + 2); }
-      e2_chunk(vb, bbv, cc + 1);
-      if (kk == 0) tmem_ld_wait(); else tc_fence_before();
-      fence_proxy_async();                                     // release the k-block to the MMA warp
+    auto release = [&](int kb, bool last) {                    // this group's slice of k-block kb is in smem
+      if (last) tc_fence_before();
+      fence_proxy_async();
       named_bar_sync(bar_id, 128);
-      if (tid == tid0) mbar_arrive_cluster(bar(BAR_H2_KB0 + (cc >> 1)), 0);
-    }
+      if (elect) mbar_arrive_cluster(bar(BAR_H2_KB0 + kb), 0);
+    };
+    const uint32_t t0 = taddr + sc * 16;
+    uint32_t v0[16], v1[16];
+    float4 b0[4], b1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) b0[q] = bfirst[q];
+    tmem_ld16(t0, v0);
+    tmem_ld_wait();
+    tmem_ld16(t0 + 64, v1);  load_b2(b1, 64 + sc * 16);  e2_sub(v0, b0, 0); tmem_ld_wait(); release(0, false);
+    tmem_ld16(t0 + 128, v0); load_b2(b0, 128 + sc * 16); e2_sub(v1, b1, 1); tmem_ld_wait(); release(1, false);
+    tmem_ld16(t0 + 192, v1); load_b2(b1, 192 + sc * 16); e2_sub(v0, b0, 2); tmem_ld_wait(); release(2, false);
+    e2_sub(v1, b1, 3);
+    release(3, true);
   };
 
-  if (warp < 4) {
-    // =========================================================== group A: layer 1 + layer-2 epilogue of acc2 columns [0,128)
-    const int row = tid;                                      // 0..127 == TMEM lane == point row of this CTA
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int grp = warp >> 2;                                  // 0,1: A0,A1 | 2,3: B0,B1 | 4: MMA warp
+  const int row = (warp & 3) * 32 + lane;                     // TMEM lane == point row (layers 1/2) == channel in chunk (layer 3)
+  const bool elect = (tid & 127) == 0;
+  const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+
+  if (grp < 2) {
+    // =========================================================== groups A0/A1: layer 1 (64 channels each) + layer-2 epilogue of
+    //                                                               k-block grp
     float xn[4] = {0.f, 0.f, 0.f, 0.f};                       // next tile's point, fetched one tile ahead (HBM latency)
     if (n_tiles > 0) load_point(x, ldx, C, tile_cloud(0), rank * PTS_PER_CTA + row, xn);
     for (int it = 0; it < n_tiles && ok; ++it) {
@@ -236,114 +245,125 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       const float xv[4] = {xn[0], xn[1], xn[2], xn[3]};
       if (it + 1 < n_tiles) load_point(x, ldx, C, tile_cloud(it + 1), ((it + 1) % tpc) * PTS_PER_TILE + rank * PTS_PER_CTA + row, xn);
       // layer 1 into registers while the previous tile's last layer-3 MMAs run
-      uint32_t h1[64];
-      layer1_part<ACT, 0, 16>(xv, sW1, sB1, h1);
+      uint32_t h1[32];
+      if (grp == 0) layer1_part<ACT, 0, 8>(xv, sW1, sB1, h1); else layer1_part<ACT, 8, 16>(xv, sW1, sB1, h1);
       if (tid == 0) TSTAMP(1);
       // the H region is still being read by the previous tile's layer-3 MMAs
       if (it > 0) ok = mbar_wait(bar(BAR_L3_DONE), (it - 1) & 1, err, 101);
       if (!ok) break;
       if (tid == 0) TSTAMP(2);
-      store_h1_part<0, 16>(smem, row, h1);
+      if (grp == 0) store_h1_part<0, 8>(smem, row, h1); else store_h1_part<8, 16>(smem, row, h1);
       fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (tid == 0) mbar_arrive_cluster(bar(BAR_H1_FULL), 0);
+      named_bar_sync(1 + grp, 128);
+      if (elect) mbar_arrive_cluster(bar(BAR_H1_FULL), 0);
       if (tid == 0) TSTAMP(3);
-      float4 ba0[8];                                          // b2 of the first chunk, in flight across the ACC2_FULL wait
-#pragma unroll
-      for (int q = 0; q < 8; ++q) ba0[q] = __ldg(reinterpret_cast<const float4*>(b2) + q);
+      float4 bf[4];                                           // b2 of the first step, in flight across the ACC2_FULL wait
+      load_b2(bf, grp * 16);
       ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 102);
       if (!ok) break;
       tc_fence_after();
       if (tid == 0) TSTAMP(4);
-      e2_half(lane_taddr + region_col(it & 1), row, 0, ba0, 1, 0);
+      e2_slices(lane_taddr + region_col(it & 1), row, grp, bf, 1 + grp, elect);
       if (tid == 0) TSTAMP(5);
     }
-  } else if (warp < 8) {
-    // =========================================================== group B: layer-2 epilogue of acc2 columns [128,256) (thread =
-    //                                                               point row), then the layer-3 epilogue (thread = output channel)
-    const int lrow = tid - 128;                               // 0..127 == TMEM lane == point row == channel within chunk
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
-    float best[2] = {-INFINITY, -INFINITY};                   // running max (key when WANT_ARGMAX: low 5 bits = 31 - column)
-    int bestp[2] = {0, 0};                                    // point index of column 0 of the winning 32-column group
+  } else if (grp < 4) {
+    // =========================================================== groups B0/B1: their slices of the layer-2 epilogue (thread =
+    //          point row), then the layer-3 epilogue (thread = channel): B0 reduces columns [0,128) of BOTH channel-chunk
+    //          accumulators, B1 columns [128,256); the two partial (max, argmax) pairs are merged once per cloud
+    const int g = grp - 2;
+    float best[2] = {-INFINITY, -INFINITY};                   // running max (key when WANT_ARGMAX: low 4 bits = 15 - column)
+    int bestp[2] = {0, 0};                                    // point index of column 0 of the winning 16-column group
+    uint4* merge = reinterpret_cast<uint4*>(scratch) + (size_t)blockIdx.x * 128;
     for (int it = 0; it < n_tiles && ok; ++it) {
       const int b = tile_cloud(it), j = it % tpc;
       {
-        float4 bb0[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bb0[q] = __ldg(reinterpret_cast<const float4*>(b2 + 128) + q);
-        if (tid == 128) TSTAMP(20);
+        float4 bf[4];
+        load_b2(bf, grp * 16);
+        if (tid == 256) TSTAMP(20);
         ok = mbar_wait(bar(BAR_ACC2_FULL), it & 1, err, 109);
         if (!ok) break;
         tc_fence_after();
-        e2_half(lane_taddr + region_col(it & 1), lrow, 4, bb0, 2, 128);
-        if (tid == 128) TSTAMP(21);
+        e2_slices(lane_taddr + region_col(it & 1), row, grp, bf, 1 + grp, elect);
+        if (tid == 256) TSTAMP(21);
       }
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {                           // layer-3 group g = channel chunk g, all 256 points of the tile
-        if (tid == 128) TSTAMP(8 + 3 * g);
-        ok = mbar_wait(bar(BAR_G_FULL0 + g), it & 1, err, 103);
+      for (int G = 0; G < 2; ++G) {                           // layer-3 group G = channel chunk G
+        if (tid == 256) TSTAMP(8 + 3 * G);
+        ok = mbar_wait(bar(BAR_G_FULL0 + G), it & 1, err, 103);
         if (!ok) break;
         tc_fence_after();
-        if (tid == 128) TSTAMP(9 + 3 * g);
-        float bv = best[g];
-        int bp = bestp[g];
+        if (tid == 256) TSTAMP(9 + 3 * G);
+        float bv = best[G];
+        int bp = bestp[G];
         {
-          auto e3_chunk = [&](uint32_t (&v)[32], int cc) {      // 32 columns (points) of this thread's channel
+          auto e3_sub = [&](uint32_t (&v)[16], int sc) {        // 16 columns (points) of this thread's channel
+            float k[16];
             if (WANT_ARGMAX) {
-              // key = value with its low 5 mantissa bits replaced by (31 - column): one FMNMX tree yields max AND position
-              // (values closer than 2^-18 relative may swap order — far below the bf16 operand rounding)
-              float k[32];
+              // key = value with its low 4 mantissa bits replaced by (15 - column): one FMNMX tree yields max AND position
+              // (values closer than 2^-19 relative may swap order — far below the bf16 operand rounding)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) k[i] = __uint_as_float((v[i] & 0xFFFFFFE0u) | (uint32_t)(31 - i));
-              const float m = max32(k);
+              for (int i = 0; i < 16; ++i) k[i] = __uint_as_float((v[i] & 0xFFFFFFF0u) | (uint32_t)(15 - i));
+              const float m = max16(k);
               // column n -> point: columns [0,128) are CTA 0's rows, [128,256) CTA 1's (the B operand's N halves)
-              const int pbase = j * PTS_PER_TILE + cc * 32;
-              if (m > bv) { bv = m; bp = pbase; }
+              if (m > bv) { bv = m; bp = j * PTS_PER_TILE + g * 128 + sc * 16; }
             } else {
-              float k[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) k[i] = __uint_as_float(v[i]);
-              bv = fmaxf(bv, max32(k));
+              for (int i = 0; i < 16; ++i) k[i] = __uint_as_float(v[i]);
+              bv = fmaxf(bv, max16(k));
             }
           };
-          const uint32_t t0 = lane_taddr + region_col((it & 1) ^ (g ^ 1));     // group 0: region p^1, group 1: region p
-          uint32_t va[32], vb[32];
-          tmem_ld32(t0, va);
+          // group 0 lives in region p^1, group 1 in region p; this epilogue group takes columns [g*128, g*128+128)
+          const uint32_t t0 = lane_taddr + region_col((it & 1) ^ (G ^ 1)) + g * 128;
+          uint32_t v0[16], v1[16];
+          tmem_ld16(t0, v0);
           tmem_ld_wait();
 #pragma unroll
           for (int c2 = 0; c2 < 4; ++c2) {
-            tmem_ld32(t0 + (2 * c2 + 1) * 32, vb); e3_chunk(va, 2 * c2); tmem_ld_wait();
-            if (c2 < 3) tmem_ld32(t0 + (2 * c2 + 2) * 32, va);
-            e3_chunk(vb, 2 * c2 + 1);
+            tmem_ld16(t0 + (2 * c2 + 1) * 16, v1); e3_sub(v0, 2 * c2); tmem_ld_wait();
+            if (c2 < 3) tmem_ld16(t0 + (2 * c2 + 2) * 16, v0);
+            e3_sub(v1, 2 * c2 + 1);
             if (c2 < 3) tmem_ld_wait();
           }
         }
-        best[g] = bv;
-        bestp[g] = bp;
+        best[G] = bv;
+        bestp[G] = bp;
         tc_fence_before();
-        named_bar_sync(2, 128);
-        if (tid == 128) mbar_arrive_cluster(bar(BAR_G_EMPTY0 + g), 0);
-        if (tid == 128) TSTAMP(10 + 3 * g);
+        named_bar_sync(1 + grp, 128);
+        if (elect) mbar_arrive_cluster(bar(BAR_G_EMPTY0 + G), 0);
+        if (tid == 256) TSTAMP(10 + 3 * G);
       }
       if (!ok) break;
-      if (j == tpc - 1) {                                     // cloud complete: pooled outputs (bias after the pool)
-#pragma unroll
-        for (int chunk = 0; chunk < 2; ++chunk) {
-          const int ch = rank * 256 + chunk * 128 + lrow;
-          const uint32_t kb = __float_as_uint(best[chunk]);
-          if (WANT_ARGMAX) {
-            feat[(int64_t)b * ldf + ch] = __uint_as_float(kb & 0xFFFFFFE0u) + __ldg(b3 + ch);
-            argmax[(int64_t)b * 512 + ch] = bestp[chunk] + 31 - (int)(kb & 31u);
-          } else {
-            feat[(int64_t)b * ldf + ch] = best[chunk] + __ldg(b3 + ch);
-          }
-          best[chunk] = -INFINITY;
-          bestp[chunk] = 0;
+      if (j == tpc - 1) {                                     // cloud complete: merge the two column halves, pooled outputs
+        if (g == 1) {
+          merge[row] = make_uint4(__float_as_uint(best[0]), (uint32_t)bestp[0], __float_as_uint(best[1]), (uint32_t)bestp[1]);
+          __threadfence_block();
         }
+        named_bar_sync(5, 256);
+        if (g == 0) {
+          const uint4 o = merge[row];
+          const float ob[2] = {__uint_as_float(o.x), __uint_as_float(o.z)};
+          const int op[2] = {(int)o.y, (int)o.w};
+#pragma unroll
+          for (int G = 0; G < 2; ++G) {
+            const bool take = ob[G] > best[G];
+            const float bv = take ? ob[G] : best[G];
+            const int bp = take ? op[G] : bestp[G];
+            const int ch = rank * 256 + G * 128 + row;
+            const uint32_t kb = __float_as_uint(bv);
+            if (WANT_ARGMAX) {
+              feat[(int64_t)b * ldf + ch] = __uint_as_float(kb & 0xFFFFFFF0u) + __ldg(b3 + ch);   // (bias after the pool)
+              argmax[(int64_t)b * 512 + ch] = bp + 15 - (int)(kb & 15u);
+            } else {
+              feat[(int64_t)b * ldf + ch] = bv + __ldg(b3 + ch);
+            }
+          }
+        }
+#pragma unroll
+        for (int G = 0; G < 2; ++G) { best[G] = -INFINITY; bestp[G] = 0; }
       }
     }
   } else if (rank == 0) {
-    // =========================================================== warp 8 of the leader CTA: MMA issue
+    // =========================================================== warp 16 of the leader CTA: MMA issue
     const uint32_t idesc = umma_idesc(256, 256);             // every MMA of this kernel: M=256 (pair), N=256, K=16
     auto l3_mma = [&](int chunk, uint32_t dcol, int k, bool acc) {   // one K=16 step of layer-3 channel chunk `chunk`
       const uint32_t koff = (k >> 2) * KBLOCK_BYTES + (k & 3) * 32;
@@ -373,7 +393,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       if (!ok) break;
 #pragma unroll 1
       for (int q = 0; q < 4 && ok; ++q) {
-        const int kb = ((q & 1) << 1) | (q >> 1);              // readiness order: k-blocks 0, 2 (first halves of A / B), then 1, 3
+        const int kb = q;                                      // (each k-block comes from its own epilogue group)
         ok = mbar_wait(bar(BAR_H2_KB0 + kb), it & 1, err, 105);
         if (!ok) break;
         tc_fence_after();
@@ -401,7 +421,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
@@ -413,7 +433,7 @@ extern "C" {
 int pm_has_tcgen05(void) { return 1; }
 
 // workspace: two packed weight images (rank 0 / rank 1) + an error word
-size_t pm_pointnet_encode_forward_tc_ws_bytes(int, int, int) { return 2 * WPACK_PER_RANK + 4096; }
+size_t pm_pointnet_encode_forward_tc_ws_bytes(int, int, int) { return 2 * WPACK_PER_RANK + 4096 + (size_t)PM_NUM_SMS * 2048; }
 
 int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int C, const pm_encoder_params* p, int act,
                                   float* feat, int64_t ldf, int32_t* argmax, void* ws, size_t ws_bytes, pm_stream_t s) {
@@ -439,9 +459,9 @@ int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int
       attr_set = true;                                                                                                      \
     }                                                                                                                       \
     if (argmax)                                                                                                             \
-      encoder_fwd_tc<ACTV, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, argmax, err); \
+      encoder_fwd_tc<ACTV, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, argmax, err, wpack + 2 * WPACK_PER_RANK + 4096); \
     else                                                                                                                    \
-      encoder_fwd_tc<ACTV, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, nullptr, err); \
+      encoder_fwd_tc<ACTV, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, nullptr, err, wpack + 2 * WPACK_PER_RANK + 4096); \
   } break;
   switch (act) {
     PM_TC_LAUNCH(PM_ACT_TANH)
