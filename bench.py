@@ -86,45 +86,56 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_iteration(E, threads, iters=1, warm=0):
+def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu"):
     """The reference's algorithm (CPU oracle port, unmodified math) for one PPO iteration at E envs; returns
-    env·steps/s on the host cores.  Only bench.py's cpu_baseline / --impl reference legs call this."""
+    env·steps/s on the host cores.  Only bench.py's cpu_baseline / --impl reference legs call this.
+    device="cuda:0" runs the same eager-PyTorch restatement on the GPU (`--impl torch_gpu`: the reference's PyTorch-GPU
+    path — fp32, TF32 off, eager — as the denominator of north_star's ">= 10x" target; not a driver arm)."""
     import torch
     from oracle import ppo_oracle as O
     torch.set_num_threads(threads)
+    on_gpu = str(device).startswith("cuda")
+    if on_gpu:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator().manual_seed(1234)
     D = N_PTS * CH
     cfg = ppo_cfg(E, "cpu", "fp32")
     net = cfg["model"]["network"]
-    actor = O.pointnet_init(D, ACT, gen=g)
-    critic = O.pointnet_init(D, 1, gen=g)
-    log_std = torch.full((ACT,), float(torch.log(torch.tensor(0.5))))
+    dv = lambda t: t.to(device)
+    actor = {k: dv(v) for k, v in O.pointnet_init(D, ACT, gen=g).items()}
+    critic = {k: dv(v) for k, v in O.pointnet_init(D, 1, gen=g).items()}
+    log_std = dv(torch.full((ACT,), float(torch.log(torch.tensor(0.5)))))
     opt_a = O.AdamState({**actor, "log_std": log_std}, cfg["lr"])
     opt_c = O.AdamState(critic, cfg["lr"])
     rs = O.RunningStats(D)
+    rs.mean, rs.S, rs.std = dv(rs.mean), dv(rs.S), dv(rs.std)
 
     def obs():
         pc = torch.rand(E, N_PTS, CH, generator=g)
         pc[..., :2] = pc[..., :2] * 2 - 1
         pc[..., 2] = pc[..., 2] * 2 + 0.05
         pc[torch.rand(E, N_PTS, generator=g) < 0.1] = 0.0
-        return pc.reshape(E, D)
+        return dv(pc.reshape(E, D))
 
     pool = [obs() for _ in range(T_STEPS + 1)]
+    rnd = lambda *sh: dv(torch.randn(*sh, generator=g))
     times = []
     for it in range(warm + iters):
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         buf = {k: [] for k in ("obs", "actions", "values", "logp", "mu", "sigma", "rew", "done")}
         with torch.no_grad():
             cur = rs.normalize(pool[0].clone(), True)
             for t in range(T_STEPS):
                 mu = O.pointnet_forward(actor, cur)
-                a, lp = O.policy_sample(mu, log_std, torch.randn(E, ACT, generator=g), 1.0)
+                a, lp = O.policy_sample(mu, log_std, rnd(E, ACT), 1.0)
                 v = O.pointnet_forward(critic, cur)
                 for k, x in zip(("obs", "actions", "values", "logp", "mu", "sigma"), (cur, a, v, lp[:, None], mu, log_std.repeat(E, 1))):
                     buf[k].append(x)
-                buf["rew"].append(torch.randn(E, 1, generator=g))
-                buf["done"].append(torch.rand(E, 1, generator=g) < 0.05)
+                buf["rew"].append(rnd(E, 1))
+                buf["done"].append(dv(torch.rand(E, 1, generator=g) < 0.05))
                 cur = rs.normalize(pool[t + 1].clone(), True)
             last = O.pointnet_forward(critic, cur)
             st = {k: torch.stack(v) for k, v in buf.items()}
@@ -133,6 +144,8 @@ def cpu_port_iteration(E, threads, iters=1, warm=0):
         b = dict(obs=flat(st["obs"]), actions=flat(st["actions"]), values=flat(st["values"]), returns=flat(ret),
                  logp=flat(st["logp"]), adv=flat(adv), mu=flat(st["mu"]), sigma=flat(st["sigma"]))
         O.ppo_update(actor, critic, log_std, opt_a, opt_c, b, cfg, "PointNet", net)
+        if on_gpu:
+            torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     t = sum(times[warm:]) / max(iters, 1)
     return E * T_STEPS / t, t
@@ -164,7 +177,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--ref-envs", type=int, default=8)
@@ -177,6 +190,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "torch_gpu":          # context only: eager PyTorch fp32 (TF32 off) on cuda:0, the reference's GPU path
+        if rank == 0:
+            v, t = cpu_port_iteration(args.envs, os.cpu_count() or 1, iters=args.steps, warm=args.warmup, device="cuda:0")
+            print(json.dumps({"impl": "torch_gpu", "metric": "env_steps_per_sec (encoder+PPO update)", "value": v,
+                              "unit": "env*steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                              "ms_per_step": t * 1e3, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": f"eager PyTorch restatement of the reference path on cuda:0, E={args.envs} envs x "
+                                                     f"{N_PTS} pts, fp32, TF32 off"}}), flush=True)
         return
 
     import torch
@@ -264,13 +286,33 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0)
     achieved_tf = B * ENC_FLOPS_PER_CLOUD / (enc_ms * 1e-3) / 1e12
-    enc_launches_per_iter = T_STEPS * 2 + 1 + 2 * 5 * (E * T_STEPS // B)
+    # encoder-forward launches per iteration: T rollout steps x (actor + critic) + the last-value critic pass, each over
+    # E clouds (E/B launch-equivalents of B clouds), + 2 networks x 5 epochs x (E*T/B) minibatches
+    enc_equiv_per_iter = (T_STEPS * 2 + 1) * (E / B) + 2 * 5 * (E * T_STEPS // B)
+    # companion kernel: encoder backward on the same minibatch
+    grads = [torch.empty_like(t) for t in enc]
+    dfeat = torch.randn(B, 512, device=dev) * 0.01
+    for i in range(2):
+        ops.pointnet_encode_backward(obs_flat[:B], N_PTS, CH, enc, "tanh", dfeat, am, grads, precision=precision)
+    k0.record()
+    for i in range(reps):
+        ops.pointnet_encode_backward(obs_flat[(i % nslices) * B:(i % nslices + 1) * B], N_PTS, CH, enc, "tanh", dfeat, am, grads,
+                                     precision=precision)
+    k1.record()
+    torch.cuda.synchronize()
+    bwd_ms = k0.elapsed_time(k1) / reps
+    # DRAM traffic of the forward kernel per launch from the committed `ncu --set full` capture
+    # (profiles/r01_fwd_r01c_metrics.txt: dram__bytes_read.sum 25.57 MB, dram__bytes_write.sum ~0: the 8 MB of outputs
+    # stay in the 126 MB L2) — the algorithmic input is B*N*C*4 = 25.17 MB
+    traffic = 25571072 if (precision == "bf16" and B == 2048) else None
     roofline = {"bound": "tensor", "kernel": "pointnet encoder forward (%s), %d clouds x %d pts per launch" % (precision, B, N_PTS),
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if peaks else "fallback 1.59 PF, of fallback",
-                "traffic": None, "ms_per_launch": enc_ms,
-                "share_of_step": enc_ms * enc_launches_per_iter * (E / B if E > B else 1.0) / ms_step if False else None,
-                "hbm_frac_for_transparency": (B * N_PTS * CH * 4 / (enc_ms * 1e-3) / 1e9) / peaks.get("hbm_gbs", 6650.0)}
+                "traffic": traffic, "algorithmic_bytes": B * N_PTS * CH * 4, "algorithmic_flops": B * ENC_FLOPS_PER_CLOUD,
+                "ms_per_launch": enc_ms, "share_of_step": enc_ms * enc_equiv_per_iter / ms_step,
+                "hbm_frac_for_transparency": (B * N_PTS * CH * 4 / (enc_ms * 1e-3) / 1e9) / peaks.get("hbm_gbs", 6650.0),
+                "companion": {"kernel": "pointnet encoder backward (%s), same minibatch" % precision, "ms_per_launch": bwd_ms,
+                              "share_of_step": bwd_ms * 2 * 5 * (E * T_STEPS // B) / ms_step}}
 
     # ---- end-to-end arm: host-resident observations, H2D copy of every step's obs + D2H of the actions inside the timed region
     e2e = None
@@ -278,8 +320,9 @@ def main():
         del runner, env
         torch.cuda.empty_cache()
         env_h, runner_h = make(host=True)
-        ms_e2e, _, _ = timed(runner_h, env_h, max(2, args.steps // 2), 1, False)
-        iters_run = max(2, args.steps // 2) + 1
+        e2e_warm = 2                                   # eager + graph-capture iterations stay outside the timed region
+        ms_e2e, _, _ = timed(runner_h, env_h, max(2, args.steps // 2), e2e_warm, False)
+        iters_run = max(2, args.steps // 2) + e2e_warm
         e2e = {"value": E * T_STEPS * world / (ms_e2e * 1e-3), "unit": "env*steps/s",
                "h2d_bytes_per_step": int(env_h.h2d_bytes / iters_run), "d2h_bytes_per_step": int(env_h.d2h_bytes / iters_run),
                "ms_per_step": ms_e2e}

@@ -167,6 +167,13 @@ class ppo:
         self.total_time = 0
         self.curr_iter = 0
         self.verbose = bool(cfg.get('verbose', False))
+        # build extension: replay the whole device-side update (160 minibatch steps at E=4096) as ONE CUDA graph.  Legal
+        # because the update has no host round trip (device-side KL-skip / step counters / loss sums) and sequential
+        # minibatches are fixed slices of persistent buffers.  First call runs eagerly (allocates workspaces), the second
+        # captures, later ones replay.  Off for the random sampler (host-side permutation) and, by default, multi-rank.
+        self.cuda_graph = bool(cfg.get('cuda_graph', True)) and cfg['sampler'] == 'sequential' and \
+            (self.world == 1 or bool(cfg.get('cuda_graph_multi_rank', False)))
+        self._graph, self._graph_calls, self._n_critic = None, 0, 0
         self.resume(cfg['resume'])
 
     # ------------------------------------------------------------------ checkpoints (ppo.py:83-137)
@@ -351,7 +358,8 @@ class ppo:
             ops.gather_rows(v, indices, out[k])
         return out
 
-    def update(self, it):
+    def _update_body(self):
+        """The device-side part of update(): both phases over all epochs and minibatches (graph-capturable)."""
         ac = self.actor_critic
         world = self.world
         self._acc.zero_()
@@ -400,8 +408,28 @@ class ppo:
                 parallel.all_reduce_sum_(self.optimizer_critic.grad)
                 self.optimizer_critic.step(None)
                 n_critic += 1
-        # ---- one read-back per iteration
         parallel.all_reduce_sum_(self._acc[4:5])
+        self._n_critic = n_critic
+
+    def update(self, it):
+        if not self.cuda_graph:
+            self._update_body()
+        elif self._graph is not None:
+            self._graph.replay()
+            ops.count_launches(self._graph_launches)      # the replay launches the same kernels the capture recorded
+        elif self._graph_calls == 0:
+            self._update_body()                       # eager warm-up: sizes every workspace, sets kernel attributes
+        else:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                self._update_body()
+            self._graph, self._graph_launches = graph, ops.launch_count() - n0
+            graph.replay()
+        self._graph_calls += 1
+        n_critic = self._n_critic
+        # ---- one read-back per iteration
         acc = self._acc.tolist()
         count = int(round(acc[2]))
         mean_value_loss = acc[4] / max(n_critic, 1)

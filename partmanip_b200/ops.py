@@ -48,6 +48,11 @@ def launch_count() -> int:
     return LAUNCHES[0]
 
 
+def count_launches(n: int):
+    """Account for kernels launched by a CUDA-graph replay of previously counted C-ABI calls."""
+    LAUNCHES[0] += int(n)
+
+
 _scratch = {}
 
 

@@ -266,3 +266,32 @@ def test_storage_overflow_and_sampler_geometry():
     s3 = RolloutStorage(64, 8, 1, 1, DEV, None, sampler="random")
     idx = torch.cat(list(s3.mini_batch_generator(8)))
     assert idx.numel() == 512 and torch.equal(idx.sort()[0].cpu(), torch.arange(512))
+
+
+def test_cuda_graph_update_is_bit_identical_to_eager():
+    """Three iterations with the update replayed as one CUDA graph (iteration 1 eager, 2 captured, 3 replayed) leave exactly
+    the weights three eager iterations leave: the kernels are deterministic and the update has no host round trip."""
+    from partmanip_b200.algorithms import ppo
+    from partmanip_b200.envs import FakeVecEnv
+    from tests.helpers import MLP128, PN, ppo_cfg
+    for net, D in ((PN, 3072), (MLP128, 53)):
+        out = []
+        for graph in (False, True):
+            torch.manual_seed(4)
+            env = FakeVecEnv(16, D, 10, DEV, cloud=net is PN, seed=8)
+            r = ppo(env, ppo_cfg(16, net, device=DEV, cuda_graph=graph, desired_kl=0.02 if net is MLP128 else 0.1, lr=1e-3 if net is MLP128 else 5e-5), _Logger())
+            curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+            g = torch.Generator().manual_seed(0)
+            for it in range(3):
+                eps = torch.randn(8, 16, 10, generator=g).to(DEV)
+                last_obs, last_values = r.collect(curr, None, eps=eps)
+                r.storage.compute_returns(last_values, r.gamma, r.lam)
+                r.update(it + 1)
+                r.storage.clear()
+                curr = r._ingest(last_obs.clone(), r.storage.obs_slot())
+            assert (r._graph is not None) == graph
+            out.append(({k: v.clone() for k, v in r.actor_critic.state_dict().items()}, dict(r.log_dict)))
+        for k in out[0][0]:
+            assert torch.equal(out[0][0][k], out[1][0][k]), k
+        for k in ("Train/surrogate_loss", "Train/value_function_loss", "Train/kl", "Train/kl_update_count"):
+            assert float(out[0][1][k]) == float(out[1][1][k]) or (out[0][1][k] != out[0][1][k]), k
