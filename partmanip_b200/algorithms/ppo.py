@@ -33,7 +33,11 @@ class FlatAdam:
 
     def __init__(self, flat, params, offsets, group_sizes, lr, n_clip, max_norm):
         self.flat, self.params, self.offsets, self.group_sizes = flat, params, offsets, group_sizes
-        self.grad = torch.zeros_like(flat)
+        # gradient buffer with a 4-float tail: per-step scalars that must be summed over ranks (sum surrogate, sum KL) ride
+        # in the SAME all-reduce as the gradients (one collective per optimiser step)
+        self.grad_ext = torch.zeros(flat.numel() + 4, device=flat.device, dtype=torch.float32)
+        self.grad = self.grad_ext[:flat.numel()]
+        self.tail = self.grad_ext[flat.numel():]
         self.exp_avg = torch.zeros_like(flat)
         self.exp_avg_sq = torch.zeros_like(flat)
         self.opt_state = torch.zeros(8, device=flat.device, dtype=torch.float32)   # [0]=step [1]=lr (device scalars)
@@ -154,7 +158,7 @@ class ppo:
         # device-side bookkeeping for one update(): acc = [sum surrogate, sum kl, count, kl_max, sum value loss]
         dev = self.device
         self._acc = torch.zeros(8, device=dev)
-        self._stats_a = torch.zeros(2, device=dev)
+        self._stats_a = self.optimizer_actor.tail[:2]     # [sum surrogate, sum KL] — reduced together with the actor gradient
         self._stats_v = torch.zeros(2, device=dev)
         self._skip = torch.zeros(1, device=dev, dtype=torch.int32)
         self._adv_stats = torch.zeros(2, device=dev)
@@ -382,10 +386,9 @@ class ppo:
                 ops.ppo_actor_loss(mu, ac.log_std.data, mb['act'], mb['logp'].reshape(-1), mb['mu'], mb['sigma'],
                                    mb['adv'].reshape(-1), adv_stats, inv_b, self.epsilon_clip, ac.max_action, squash,
                                    self._stats_a, dmu, self._actor_grads[-1])
-                parallel.all_reduce_sum_(self._stats_a)      # rank-consistent KL-skip decision
-                ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)
                 ac.actor.runner.backward(mb['obs'], dmu, self._actor_grads[:-1])
-                parallel.all_reduce_sum_(self.optimizer_actor.grad)
+                parallel.all_reduce_sum_(self.optimizer_actor.grad_ext)   # gradients + [sum surrogate, sum KL] in one collective
+                ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)   # rank-consistent KL-skip
                 self.optimizer_actor.step(self._skip)
         # ---- phase 2: critic (ppo.py:359-384)
         n_critic = 0
