@@ -161,14 +161,22 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     for (int i = 0; i < 128; ++i) acc3[i] = 0.f;
     float db3 = 0.f, db2 = 0.f, dw1[4] = {0.f, 0.f, 0.f, 0.f}, db1 = 0.f;
 
-    // statically indexed (C <= 4 predicated loads) so the prefetched values stay in registers and in flight
-    auto load_row = [&](int pair, float& g, float& x0, float& x1, float& x2, float& x3) {
-      const int b = 2 * pair + par;
-      g = 0.f; x0 = x1 = x2 = x3 = 0.f;
-      if (b < B) {
-        int n = __ldg(argmax + (int64_t)b * 512 + c);
-        n = min(max(n, 0), N - 1);
+    // Two-deep prefetch so neither global latency is exposed: (argmax index, dfeat) of tile it+2 and — with the index
+    // fetched one tile earlier — the point of tile it+1.  Statically indexed (C <= 4 predicated loads) so the values stay in
+    // registers and in flight.
+    auto load_idx = [&](int t, int& n, float& g) {
+      const int b = 2 * (slab + t * n_slabs) + par;
+      n = 0; g = 0.f;
+      if (t < n_tiles && b < B) {
+        n = __ldg(argmax + (int64_t)b * 512 + c);
         g = __ldg(dfeat + (int64_t)b * lddf + c);
+      }
+    };
+    auto load_x = [&](int t, int n, float& x0, float& x1, float& x2, float& x3) {
+      const int b = 2 * (slab + t * n_slabs) + par;
+      x0 = x1 = x2 = x3 = 0.f;
+      if (t < n_tiles && b < B) {
+        n = min(max(n, 0), N - 1);
         const float* xp = x + (int64_t)b * ldx + (int64_t)n * C;
         x0 = __ldg(xp);
         if (C > 1) x1 = __ldg(xp + 1);
@@ -176,13 +184,22 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         if (C > 3) x3 = __ldg(xp + 3);
       }
     };
-    float g_nxt = 0.f, xn0 = 0.f, xn1 = 0.f, xn2 = 0.f, xn3 = 0.f;
-    if (n_tiles > 0) load_row(slab, g_nxt, xn0, xn1, xn2, xn3);
+    int n1 = 0, n2 = 0;                       // argmax index of tile it+1 / it+2
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;       // dfeat of tile it / it+1 / it+2
+    float xn0 = 0.f, xn1 = 0.f, xn2 = 0.f, xn3 = 0.f;
+    {
+      int n0;
+      load_idx(0, n0, g0);
+      load_idx(1, n1, g1);
+      load_x(0, n0, xn0, xn1, xn2, xn3);
+    }
 
     for (int it = 0; it < n_tiles && ok; ++it) {
-      const float g = g_nxt;
+      const float g = g0;
       const float xv[4] = {xn0, xn1, xn2, xn3};
-      if (it + 1 < n_tiles) load_row(slab + (it + 1) * n_slabs, g_nxt, xn0, xn1, xn2, xn3);   // prefetch the next tile's row
+      load_idx(it + 2, n2, g2);                                   // prefetch: index two tiles ahead ...
+      load_x(it + 1, n1, xn0, xn1, xn2, xn3);                     // ... and the next tile's point through last tile's index
+      g0 = g1; g1 = g2; n1 = n2;
       BSTAMP(0);
       // ---- S1: layer 1 for this thread's 64 channels (= one k-block of H1)
       {

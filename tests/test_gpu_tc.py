@@ -99,3 +99,47 @@ def test_tc_encoder_backward_vs_autograd(B, N, C, act):
         assert rel < (1e-2 if act != "relu" else 8e-2), (k, rel)
     # mlp.4.bias is a plain sum of dfeat: exact up to fp32 summation order
     assert float((grads[5].cpu() - p["mlp.4.bias"].grad).abs().max()) <= 1e-5 * float(dfeat.abs().sum(0).max()) + 1e-7
+
+
+def test_tc_pointnet_submean_proprio_golden_bf16():
+    """bf16 mode through the full network with in-place centring (Q3) and a proprio tail (F = 537): outputs within the
+    1e-2 gate of the reference recording, the caller's tensor centred exactly like the reference centres it."""
+    if not _has_tc():
+        pytest.skip("library built without the tcgen05 encoder")
+    from partmanip_b200.algorithms.algo_utils.network import PointNet
+    g = load_golden("pointnet_submean_proprio.npz")
+    p = int(sub(g, "w")["final_mlp.0.weight"].shape[1]) - 512
+    net = PointNet(int(g["x"].shape[1]), int(g["y"].shape[1]), dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=True,
+                                                                     precision="bf16"), p)
+    net.load_state_dict(sub(g, "w"))
+    net.to(DEV)
+    x = cu(g["x"])
+    y = net(x)
+    assert close(y.detach().cpu(), g["y"], 1e-2, 1e-2), max_err(y.detach().cpu(), g["y"])
+    assert close(x.cpu(), g["x_after"], 1e-5, 1e-6)
+    y.square().sum().backward()
+    for k, v in sub(g, "g").items():
+        got = dict(net.named_parameters())[k].grad.cpu()
+        assert bool(torch.isfinite(got).all()) and float((got - v).norm() / (v.norm() + 1e-12)) < 0.15, k
+
+
+def test_tc_unsupported_shapes_fail_loudly():
+    """The tcgen05 path has shape limits (N multiple of 256, C <= 4); outside them the C-ABI returns an error code and a
+    message (no silent fallback) and the fp32 path serves the shape."""
+    from partmanip_b200 import ops
+    from partmanip_b200._lib import PMError
+    p = O.pointnet_init(1000 * 3, 10, point_num=1000, gen=torch.Generator().manual_seed(1))
+    enc = [cu(p[k]) for k in NAMES]
+    x = cu(torch.rand(2, 3000))
+    feat = torch.empty(2, 512, device=DEV)
+    am = torch.empty(2, 512, device=DEV, dtype=torch.int32)
+    with pytest.raises(PMError, match="multiple of 256"):
+        ops.pointnet_encode_forward(x, 1000, 3, enc, "tanh", "bf16", feat, None, am, None)
+    ops.pointnet_encode_forward(x, 1000, 3, enc, "tanh", "fp32", feat, None, am, None)
+    want = O.pointnet_encode(p, x.cpu().view(2, 1000, 3)).max(dim=1)[0]
+    assert close(feat.cpu(), want, 1e-4, 1e-5)
+    p6 = O.pointnet_init(256 * 6, 10, point_num=256, gen=torch.Generator().manual_seed(1))
+    with pytest.raises(PMError, match="channels per point"):
+        ops.pointnet_encode_forward(cu(torch.rand(2, 1536)), 256, 6, [cu(p6[k]) for k in NAMES], "tanh", "bf16", feat, None, am, None)
+    with pytest.raises(ValueError):
+        ops.pointnet_encode_forward(torch.rand(2, 3000), 1000, 3, enc, "tanh", "fp32", feat, None, am, None)   # CPU tensor
