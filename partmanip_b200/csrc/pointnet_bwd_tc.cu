@@ -15,7 +15,9 @@
 //   M3  tcgen05    : dH1[128 x 128] = dPre2 . W2       (A K-major, B = the same W2 image read MN-major)   cols [0,128)
 //   M2  tcgen05    : dW2[256 x 128] += dPre2^T . H1    (both operands MN-major views of the smem tiles above;
 //                    accumulated in TMEM cols [256,512) across ALL tiles of the CTA)
-//   S3  8 warps    : dPre1 = dH1 * act'(H1) -> smem; column sums on CUDA cores: db2 (from dPre2), dW1/db1 (from dPre1, x)
+//   S3  8 warps    : dPre1 = dH1 * act'(H1) -> smem (in place over H1)
+//   M5/M4 tcgen05  : the column sums as N=16 MMAs against Xe = [x | 1 | 0..] (bf16, MN-major, no swizzle):
+//                    dPre2^T . Xe -> db2 (the ones column), dPre1^T . Xe -> dW1 | db1; read back per tile (1 tcgen05.ld each)
 // Per-CTA partial gradients go to the workspace; a fixed-order reduce kernel produces the six gradient tensors.
 // HBM traffic per minibatch: argmax + dfeat (4 KB/cloud) + 12 B per row gathered + ~40 MB of partials.
 #include "tc_common.cuh"
@@ -36,23 +38,27 @@ constexpr uint32_t SB_W2 = 0;            // bf16 W2 [256 h2 x 128 h1], K-major S
 constexpr uint32_t SB_H1 = 65536;        // bf16 H1 / dPre1 [128 rows x 128]: 2 k-blocks x 16 KB                   = 32768
 constexpr uint32_t SB_DP2 = 98304;       // bf16 dPre2 [128 rows x 256]: 4 k-blocks x 16 KB                         = 65536
 constexpr uint32_t SB_W3 = 163840;       // bf16x2 W3 block [128 k-pairs][64 ch]                                    = 32768
-constexpr uint32_t SB_XS = 196608;       // float4 x rows [128]                                                     =  2048
-constexpr uint32_t SB_W1 = 198656;       // float4 W1 rows [128]                                                    =  2048
-constexpr uint32_t SB_B1 = 200704;       // fp32 b1 [128]                                                           =   512
-constexpr uint32_t SB_B2 = 201216;       // fp32 b2 [256]                                                           =  1024
-constexpr uint32_t SB_BAR = 202240;      // 4 mbarriers + tmem slot
-constexpr uint32_t SB_TOTAL = 202240 + 64;
+constexpr uint32_t SB_XE = 196608;       // bf16 Xe [128 rows x 16]: cols 0..C-1 = x, col C = 1, rest 0; MN-major, no swizzle:
+                                         // 8-row x 8-col core matrices (128 B), N blocks 128 B apart, K groups 256 B apart =  4096
+constexpr uint32_t SB_W1 = 200704;       // float4 W1 rows [128]                                                    =  2048
+constexpr uint32_t SB_B1 = 202752;       // fp32 b1 [128]                                                           =   512
+constexpr uint32_t SB_B2 = 203264;       // fp32 b2 [256]                                                           =  1024
+constexpr uint32_t SB_BAR = 204288;      // 4 mbarriers + tmem slot
+constexpr uint32_t SB_TOTAL = 204288 + 64;
+// transient N=16 accumulators inside the (free after S2 / S3) upper half of the D2 region
+constexpr uint32_t TC_DB2 = 128;         // + hh*16: dPre2^T . Xe for h2-channel half hh
+constexpr uint32_t TC_DW1 = 160;         // dPre1^T . Xe
 
-enum { BAR_ACC2_FULL = 0, BAR_ACC1_FULL, NUM_BARS };
+enum { BAR_ACC2_FULL = 0, BAR_ACC1_FULL, BAR_M4_FULL, NUM_BARS };
 
 // ---- per-CTA partial-gradient record (floats)
 constexpr int PW2 = 0;                   // [256][128]
 constexpr int PW3 = 32768;               // [2 cloud parities][64 ch][256]
 constexpr int PB3 = 65536;               // [2][64]
 constexpr int PB2 = 65664;               // [256]
-constexpr int PW1 = 65920;               // [2 row halves][128][4]
-constexpr int PB1 = 66944;               // [2][128]
-constexpr int PART_FLOATS = 67200;
+constexpr int PW1 = 65920;               // [128][4]
+constexpr int PB1 = 66432;               // [128]
+constexpr int PART_FLOATS = 66560;
 
 constexpr size_t W2IMG_BYTES = 65536;
 constexpr size_t W3PACK_BYTES = (size_t)NCB * 32768;
@@ -106,7 +112,6 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   const int P = (B + 1) >> 1;                                     // cloud pairs
   const int n_tiles = slab < P ? (P - slab + n_slabs - 1) / n_slabs : 0;
   float* part = part_all + (size_t)j * PART_FLOATS;
-  float4* sXs = reinterpret_cast<float4*>(smem + SB_XS);
   float4* sW1 = reinterpret_cast<float4*>(smem + SB_W1);
   float* sB1 = reinterpret_cast<float*>(smem + SB_B1);
   float* sB2 = reinterpret_cast<float*>(smem + SB_B2);
@@ -130,6 +135,7 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       sB1[i] = b1[i];
     }
     for (int i = tid; i < 256; i += BT_THREADS) sB2[i] = b2[i];
+    for (int i = tid; i < 4096 / 16; i += BT_THREADS) reinterpret_cast<uint4*>(smem + SB_XE)[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (tid == 0) {
     for (int i = 0; i < NUM_BARS; ++i) mbar_init(bar(i), 1);
@@ -149,6 +155,7 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   const uint32_t idesc_m1 = umma_idesc_ex(128, 256, 0, 0);
   const uint32_t idesc_m3 = umma_idesc_ex(128, 128, 0, 1);
   const uint32_t idesc_m2 = umma_idesc_ex(128, 128, 1, 1);
+  const uint32_t idesc_m45 = umma_idesc_ex(128, 16, 1, 1);
   {
     // =========================================================== thread = (row r, column half hsel)
     const int q = warp & 3, hsel = warp >> 2;
@@ -216,7 +223,12 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         for (int c8 = 0; c8 < 8; ++c8)
           *reinterpret_cast<uint4*>(smem + SB_H1 + hsel * KB16 + sw128(r, c8)) =
               make_uint4(h1[4 * c8], h1[4 * c8 + 1], h1[4 * c8 + 2], h1[4 * c8 + 3]);
-        if (hsel == 0) { sXs[r] = make_float4(xv[0], xv[1], xv[2], xv[3]); db3 += g; }
+        if (hsel == 0) {                                           // Xe row r: [x_0..x_{C-1}, 1, 0, ...] in bf16 (first 8 columns)
+          const float e1 = C == 1 ? 1.f : xv[1], e2 = C == 2 ? 1.f : xv[2], e3 = C == 3 ? 1.f : xv[3], e4 = C == 4 ? 1.f : 0.f;
+          *reinterpret_cast<uint4*>(smem + SB_XE + (r >> 3) * 256 + (r & 7) * 16) =
+              make_uint4(pack_bf16(xv[0], e1), pack_bf16(e2, e3), pack_bf16(e4, 0.f), 0u);
+          db3 += g;
+        }
       }
       fence_proxy_async();
       BSTAMP(1);
@@ -278,6 +290,14 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {                         // M5: dPre2^T . Xe (N = 16): column C is db2 of this tile
+            umma_bf16_1cta(tmem_base + TC_DB2 + hh * 16, umma_desc_mn(sbase + SB_DP2 + hh * 2 * KB16 + ks * 2048, KB16, 1024),
+                           umma_desc_mn_noswz(sbase + SB_XE + ks * 512, 256, 128), idesc_m45, ks > 0);
+          }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
           for (int ks = 0; ks < 8; ++ks) {                         // M2: K = 128 rows; A = dPre2^T, B = H1, both MN-major
             umma_bf16_1cta(tmem_base + 256 + hh * 128, umma_desc_mn(sbase + SB_DP2 + hh * 2 * KB16 + ks * 2048, KB16, 1024),
                            umma_desc_mn(sbase + SB_H1 + ks * 2048, KB16, 1024), idesc_m2, (it > 0 || ks > 0) ? 1u : 0u);
@@ -287,27 +307,18 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       }
       __syncwarp();
       BSTAMP(7);
-      // ---- db2 column sums over the tile (thread tid owns h2 channel tid) while the MMAs run
-      {
-        const uint32_t base = SB_DP2 + (tid >> 6) * KB16 + (tid & 7) * 2;
-        const uint32_t c8 = (tid & 63) >> 3;
-        float s = 0.f;
-#pragma unroll 4
-        for (int r8 = 0; r8 < 16; ++r8) {
-#pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const uint16_t hv = *reinterpret_cast<const uint16_t*>(smem + base + (r8 * 8 + rr) * 128 + ((c8 ^ rr) << 4));
-            s += __uint_as_float((uint32_t)hv << 16);
-          }
-        }
-        db2 += s;
-      }
       BSTAMP(8);
       // ---- S3: dPre1 = dH1 * act'(H1), in place over H1
       ok = mbar_wait(bar(BAR_ACC1_FULL), it & 1, err, 202);
       if (!ok) break;
       tc_fence_after();
       BSTAMP(9);
+      {                                                            // db2 of this tile: lane = h2 channel hsel*128 + r, column C
+        uint32_t v[16];
+        tmem_ld16(lane_taddr + TC_DB2 + hsel * 16, v);
+        tmem_ld_wait();
+        db2 += __uint_as_float(C == 1 ? v[1] : (C == 2 ? v[2] : (C == 3 ? v[3] : v[4])));
+      }
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
@@ -329,28 +340,33 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         }
       }
       tc_fence_before();
+      fence_proxy_async();
       BSTAMP(10);
       __syncthreads();
       BSTAMP(11);
-      // ---- dW1 / db1 column sums (thread owns h1 channel tid&127 over row half tid>>7)
-      {
-        const int jc = tid & 127, half = tid >> 7;
-        const uint32_t base = SB_H1 + (jc >> 6) * KB16 + (jc & 7) * 2;
-        const uint32_t c8 = (jc & 63) >> 3;
-#pragma unroll 2
-        for (int r8 = 0; r8 < 8; ++r8) {
+      // ---- M4: dPre1^T . Xe (M = 128 h1 channels, N = 16, K = 128 rows): columns 0..C-1 = dW1, column C = db1 of this tile
+      fence_proxy_async();
+      if (tid == 0) {
+        tc_fence_after();
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int row = half * 64 + r8 * 8 + rr;
-            const uint16_t hv = *reinterpret_cast<const uint16_t*>(smem + base + row * 128 + ((c8 ^ rr) << 4));
-            const float d = __uint_as_float((uint32_t)hv << 16);
-            const float4 xs = sXs[row];
-            dw1[0] = fmaf(d, xs.x, dw1[0]); dw1[1] = fmaf(d, xs.y, dw1[1]);
-            dw1[2] = fmaf(d, xs.z, dw1[2]); dw1[3] = fmaf(d, xs.w, dw1[3]);
-            db1 += d;
-          }
-        }
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16_1cta(tmem_base + TC_DW1, umma_desc_mn(sbase + SB_H1 + ks * 2048, KB16, 1024),
+                         umma_desc_mn_noswz(sbase + SB_XE + ks * 512, 256, 128), idesc_m45, ks > 0);
+        umma_commit_1cta(bar(BAR_M4_FULL));
       }
+      __syncwarp();
+      ok = mbar_wait(bar(BAR_M4_FULL), it & 1, err, 206);
+      if (!ok) break;
+      tc_fence_after();
+      if (hsel == 0) {                                             // lane = h1 channel r
+        uint32_t v[16];
+        tmem_ld16(lane_taddr + TC_DW1, v);
+        tmem_ld_wait();
+        dw1[0] += __uint_as_float(v[0]); dw1[1] += __uint_as_float(v[1]);
+        dw1[2] += __uint_as_float(v[2]); dw1[3] += __uint_as_float(v[3]);
+        db1 += __uint_as_float(C == 1 ? v[1] : (C == 2 ? v[2] : (C == 3 ? v[3] : v[4])));
+      }
+      tc_fence_before();
       BSTAMP(12);
       __syncthreads();                                             // H1 / Xs / dPre2 free for the next tile
       BSTAMP(13);
@@ -382,9 +398,11 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
 #pragma unroll
       for (int i = 0; i < 32; ++i) d3[i] = make_float4(acc3[4 * i], acc3[4 * i + 1], acc3[4 * i + 2], acc3[4 * i + 3]);
       if (hsel == 0) part[PB3 + par * 64 + ch] = db3;
-      part[PB2 + tid] = db2;
-      reinterpret_cast<float4*>(part + PW1)[(tid >> 7) * 128 + (tid & 127)] = make_float4(dw1[0], dw1[1], dw1[2], dw1[3]);
-      part[PB1 + (tid >> 7) * 128 + (tid & 127)] = db1;
+      part[PB2 + hsel * 128 + r] = db2;
+      if (hsel == 0) {
+        reinterpret_cast<float4*>(part + PW1)[r] = make_float4(dw1[0], dw1[1], dw1[2], dw1[3]);
+        part[PB1 + r] = db1;
+      }
     }
   }
 
@@ -442,8 +460,7 @@ reduce_bwd_partials_kernel(const float* __restrict__ part, int G, int C, pm_enco
     if (cc >= C) return;
     float t = 0.f;
     for (int j = 0; j < G; ++j) {
-      const float* p = part + (size_t)j * PART_FLOATS + PW1 + ch * 4 + cc;
-      t += p[0] + p[128 * 4];
+      t += part[(size_t)j * PART_FLOATS + PW1 + ch * 4 + cc];
     }
     g.W1[ch * C + cc] = t;
     return;
@@ -452,8 +469,7 @@ reduce_bwd_partials_kernel(const float* __restrict__ part, int G, int C, pm_enco
   if (i < 128) {
     float t = 0.f;
     for (int j = 0; j < G; ++j) {
-      const float* p = part + (size_t)j * PART_FLOATS + PB1 + i;
-      t += p[0] + p[128];
+      t += part[(size_t)j * PART_FLOATS + PB1 + i];
     }
     g.b1[i] = t;
   }

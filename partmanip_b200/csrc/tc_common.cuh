@@ -123,6 +123,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lb
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major, NO swizzle (cute::UMMA LayoutType::INTERLEAVE): 8 (K rows) x 8 (MN elements) core matrices of 128 B, a K row =
+// 16 contiguous bytes; core matrices `sbo` bytes apart along MN and `lbo` bytes apart along K
+__device__ __forceinline__ uint64_t umma_desc_mn_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
 // instruction descriptor with operand majors: bit 15 = A is MN-major, bit 16 = B is MN-major
 __host__ __device__ constexpr uint32_t umma_idesc_ex(int M, int N, int a_mn, int b_mn) {
   return umma_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);

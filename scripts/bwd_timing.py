@@ -20,8 +20,8 @@ torch.cuda.synchronize()
 ws = ops._scratch[(dev, "encbwd_bf16")]
 off = 65536 + 8 * 32768 + 64
 d = ws[off:off + 64 * 8].view(torch.int64).cpu()
-lab = ["tile start", "S1 done", "sync1 passed", "(issuer) M1 issued", "ACC2_FULL ok", "S2 done", "sync2 passed", "-", "db2 sums done",
-       "ACC1_FULL ok (M3 done)", "S3 done (incl. M2 wait)", "sync3 passed", "dW1 sums done", "sync4 passed (tile end)"]
+lab = ["tile start", "S1 done", "sync1 passed", "M1 issued", "ACC2_FULL ok", "S2 done", "sync2 passed", "M3+M5+M2 issued", "-",
+       "ACC1_FULL ok", "S3 done", "sync3 passed", "M4 done + read back", "sync4 passed (tile end)"]
 base = int(d[0])
 for i, l in enumerate(lab):
     if l != "-": print(f"{int(d[i]) - base:8d}  {l}")
