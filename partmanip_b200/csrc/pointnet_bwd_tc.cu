@@ -191,6 +191,17 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
         if (C > 3) x3 = __ldg(xp + 3);
       }
     };
+    uint32_t h1[32];                          // H1 row of the current (or, once precomputed, the next) tile, packed bf16x2
+    auto layer1 = [&](const float (&xv)[4], uint32_t (&h)[32]) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = hsel * 64 + 2 * i;
+        const float4 w0 = sW1[k], w1 = sW1[k + 1];
+        const float a0 = fmaf(xv[3], w0.w, fmaf(xv[2], w0.z, fmaf(xv[1], w0.y, fmaf(xv[0], w0.x, sB1[k]))));
+        const float a1 = fmaf(xv[3], w1.w, fmaf(xv[2], w1.z, fmaf(xv[1], w1.y, fmaf(xv[0], w1.x, sB1[k + 1]))));
+        h[i] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
+      }
+    };
     int n1 = 0, n2 = 0;                       // argmax index of tile it+1 / it+2
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;       // dfeat of tile it / it+1 / it+2
     float xn0 = 0.f, xn1 = 0.f, xn2 = 0.f, xn3 = 0.f;
@@ -208,17 +219,10 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       load_x(it + 1, n1, xn0, xn1, xn2, xn3);                     // ... and the next tile's point through last tile's index
       g0 = g1; g1 = g2; n1 = n2;
       BSTAMP(0);
-      // ---- S1: layer 1 for this thread's 64 channels (= one k-block of H1)
+      // ---- S1: layer 1 for this thread's 64 channels (= one k-block of H1).  Warps 1-7 computed it one tile early, while
+      //      the tensor core ran M3/M5/M2 (see below); warp 0 was busy issuing those MMAs and does it here.
       {
-        uint32_t h1[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = hsel * 64 + 2 * i;
-          const float4 w0 = sW1[k], w1 = sW1[k + 1];
-          const float a0 = fmaf(xv[3], w0.w, fmaf(xv[2], w0.z, fmaf(xv[1], w0.y, fmaf(xv[0], w0.x, sB1[k]))));
-          const float a1 = fmaf(xv[3], w1.w, fmaf(xv[2], w1.z, fmaf(xv[1], w1.y, fmaf(xv[0], w1.x, sB1[k + 1]))));
-          h1[i] = pack_bf16(act_fast<ACT>(a0), act_fast<ACT>(a1));
-        }
+        if (it == 0 || warp == 0) layer1(xv, h1);
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8)
           *reinterpret_cast<uint4*>(smem + SB_H1 + hsel * KB16 + sw128(r, c8)) =
@@ -307,6 +311,10 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       }
       __syncwarp();
       BSTAMP(7);
+      if (warp != 0 && it + 1 < n_tiles) {                         // next tile's layer 1 under the MMAs (its point is prefetched)
+        const float xnext[4] = {xn0, xn1, xn2, xn3};
+        layer1(xnext, h1);
+      }
       BSTAMP(8);
       // ---- S3: dPre1 = dH1 * act'(H1), in place over H1
       ok = mbar_wait(bar(BAR_ACC1_FULL), it & 1, err, 202);
