@@ -12,10 +12,11 @@
 namespace {
 
 constexpr int HR = 16;            // batch rows per CTA
-constexpr int HT = 256;           // threads
+constexpr int HT = 256;           // threads (backward kernels)
+constexpr int HF = 512;           // threads of the forward kernel: 4 warps per scheduler hide the LDS / L2 latencies (2 ran at IPC 0.26)
 constexpr int H1D = 128, H2D = 32, OMAX = 32;
 constexpr int KC = 32;            // k-chunk of layer 0
-constexpr int RB = 128;           // rows per slab in bwd_b
+constexpr int RB = 64;            // rows per slab in bwd_b (256 CTAs at B = 2048: two per SM)
 constexpr int CBK = 64;           // columns per CTA in bwd_b
 
 // per-CTA partial record of bwd_a (floats)
@@ -36,79 +37,66 @@ struct FwdS {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(HT)
+__global__ void __launch_bounds__(HF)
 head_fwd_kernel(const float* __restrict__ feat, int64_t ldf, int B, int F, pm_head_params P, int out_dim,
                 float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ out, int64_t ldo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FwdS& S = *reinterpret_cast<FwdS*>(smem_raw);
   const int t = threadIdx.x, row0 = blockIdx.x * HR;
-  for (int i = t; i < H2D * H1D; i += HT) S.W1s[i >> 7][i & 127] = P.W1[i];
-  for (int i = t; i < out_dim * H2D; i += HT) S.W2s[i >> 5][i & 31] = P.W2[i];
-  // ---- layer 0: thread = (column n, 8-row group rg)
+  for (int i = t; i < H2D * H1D; i += HF) S.W1s[i >> 7][i & 127] = P.W1[i];
+  for (int i = t; i < out_dim * H2D; i += HF) S.W2s[i >> 5][i & 31] = P.W2[i];
+  // ---- layer 0: thread = (column n, 4-row group rg)
   const int n = t & 127, rg = t >> 7;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  float wreg[16], freg[2];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float wreg[8], freg;
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int idx = t + i * HT, nn = idx >> 5, kk = idx & 31;
+    for (int i = 0; i < 8; ++i) {
+      const int idx = t + i * HF, nn = idx >> 5, kk = idx & 31;
       wreg[i] = (k0 + kk < F) ? __ldg(P.W0 + (int64_t)nn * F + k0 + kk) : 0.f;
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = t + i * HT, r = idx >> 5, kk = idx & 31;
-      freg[i] = (row0 + r < B && k0 + kk < F) ? __ldg(feat + (int64_t)(row0 + r) * ldf + k0 + kk) : 0.f;
-    }
+    const int r = t >> 5, kk = t & 31;
+    freg = (row0 + r < B && k0 + kk < F) ? __ldg(feat + (int64_t)(row0 + r) * ldf + k0 + kk) : 0.f;
   };
   fetch(0);
   for (int k0 = 0; k0 < F; k0 += KC) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { const int idx = t + i * HT; S.Ws[idx >> 5][idx & 31] = wreg[i]; }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { const int idx = t + i * HT; S.Fs[idx & 31][idx >> 5] = freg[i]; }
+    for (int i = 0; i < 8; ++i) { const int idx = t + i * HF; S.Ws[idx >> 5][idx & 31] = wreg[i]; }
+    S.Fs[t & 31][t >> 5] = freg;
     __syncthreads();
     if (k0 + KC < F) fetch(k0 + KC);
 #pragma unroll
     for (int kk = 0; kk < KC; ++kk) {
       const float w = S.Ws[n][kk];
-      const float4 f0 = *reinterpret_cast<const float4*>(&S.Fs[kk][rg * 8]);
-      const float4 f1 = *reinterpret_cast<const float4*>(&S.Fs[kk][rg * 8 + 4]);
+      const float4 f0 = *reinterpret_cast<const float4*>(&S.Fs[kk][rg * 4]);
       acc[0] = fmaf(w, f0.x, acc[0]); acc[1] = fmaf(w, f0.y, acc[1]); acc[2] = fmaf(w, f0.z, acc[2]); acc[3] = fmaf(w, f0.w, acc[3]);
-      acc[4] = fmaf(w, f1.x, acc[4]); acc[5] = fmaf(w, f1.y, acc[5]); acc[6] = fmaf(w, f1.z, acc[6]); acc[7] = fmaf(w, f1.w, acc[7]);
     }
     __syncthreads();
   }
   {
     const float bb = P.b0[n];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rg * 8 + i;
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
       const float v = pm_act_fwd(ACT, acc[i] + bb);
       S.H1s[r][n] = v;
       if (row0 + r < B) h1[(int64_t)(row0 + r) * H1D + n] = v;
     }
   }
   __syncthreads();
-  // ---- layer 1: thread = (column m, rows rr and rr+8)
+  // ---- layer 1: thread = (column m, row rr)
   {
     const int m = t & 31, rr = t >> 5;
-    float a0 = P.b1[m], a1 = a0;
+    float a0 = P.b1[m];
 #pragma unroll 8
-    for (int k = 0; k < H1D; ++k) {
-      const float w = S.W1s[m][k];
-      a0 = fmaf(w, S.H1s[rr][k], a0);
-      a1 = fmaf(w, S.H1s[rr + 8][k], a1);
-    }
-    a0 = pm_act_fwd(ACT, a0); a1 = pm_act_fwd(ACT, a1);
-    S.H2s[rr][m] = a0; S.H2s[rr + 8][m] = a1;
+    for (int k = 0; k < H1D; ++k) a0 = fmaf(S.W1s[m][k], S.H1s[rr][k], a0);
+    a0 = pm_act_fwd(ACT, a0);
+    S.H2s[rr][m] = a0;
     if (row0 + rr < B) h2[(int64_t)(row0 + rr) * H2D + m] = a0;
-    if (row0 + rr + 8 < B) h2[(int64_t)(row0 + rr + 8) * H2D + m] = a1;
   }
   __syncthreads();
   // ---- layer 2 (no activation)
-  for (int i = t; i < HR * out_dim; i += HT) {
+  for (int i = t; i < HR * out_dim; i += HF) {
     const int r = i / out_dim, o = i - r * out_dim;
     float a = P.b2[o];
 #pragma unroll
@@ -350,7 +338,7 @@ int pm_pointnet_head_forward(const float* feat, int64_t ldf, int B, int F, const
       if (e != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));                     \
       attr_set = true;                                                                                                   \
     }                                                                                                                    \
-    head_fwd_kernel<ACTV><<<pm_cdiv(B, HR), HT, sizeof(FwdS), pm_st(s)>>>(feat, ldf, B, F, *p, out_dim, h1, h2, out, ldo); \
+    head_fwd_kernel<ACTV><<<pm_cdiv(B, HR), HF, sizeof(FwdS), pm_st(s)>>>(feat, ldf, B, F, *p, out_dim, h1, h2, out, ldo); \
   } break;
   switch (act) {
     PM_HF(PM_ACT_NONE) PM_HF(PM_ACT_TANH) PM_HF(PM_ACT_RELU) PM_HF(PM_ACT_ELU) PM_HF(PM_ACT_SELU) PM_HF(PM_ACT_LRELU)

@@ -143,3 +143,50 @@ def test_tc_unsupported_shapes_fail_loudly():
         ops.pointnet_encode_forward(cu(torch.rand(2, 1536)), 256, 6, [cu(p6[k]) for k in NAMES], "tanh", "bf16", feat, None, am, None)
     with pytest.raises(ValueError):
         ops.pointnet_encode_forward(torch.rand(2, 3000), 1000, 3, enc, "tanh", "fp32", feat, None, am, None)   # CPU tensor
+
+
+def test_tc_encoder_full_size_properties():
+    """BASELINE config-2 minibatch (2048 clouds x 1024 pts) through size-independent properties: (1) a random subset of
+    clouds against the oracle, (2) the symmetric pool is exactly invariant to the order of the points of a cloud (argmax
+    follows the permutation), (3) a cloud's features do not depend on which other clouds share the launch."""
+    if not _has_tc():
+        pytest.skip("library built without the tcgen05 encoder")
+    from partmanip_b200 import ops
+    torch.manual_seed(11)
+    B, N, C = 2048, 1024, 3
+    x = torch.rand(B, N, C) * 2 - 1
+    x[:, ::11] = 0.0
+    p = O.pointnet_init(N * C, 10, gen=torch.Generator().manual_seed(4))
+    enc = [cu(p[k]) for k in NAMES]
+    xd = cu(x.reshape(B, N * C))
+    feat = torch.empty(B, 512, device=DEV)
+    am = torch.empty(B, 512, device=DEV, dtype=torch.int32)
+    ops.pointnet_encode_forward(xd, N, C, enc, "tanh", "bf16", feat, None, am, None)
+    assert ops.pointnet_tc_last_error(DEV) == 0
+    # (1) subset parity
+    idx = torch.randint(0, B, (8,))
+    want = O.pointnet_encode(p, x[idx]).max(dim=1)[0]
+    assert close(feat[idx.to(DEV)].cpu(), want, 1e-2, 1e-2), max_err(feat[idx.to(DEV)].cpu(), want)
+    # (2) permutation invariance (exact: every point goes through identical arithmetic wherever it sits)
+    perm = torch.randperm(N)
+    xp = cu(x[:, perm].reshape(B, N * C))
+    feat_p = torch.empty_like(feat)
+    am_p = torch.empty_like(am)
+    ops.pointnet_encode_forward(xp, N, C, enc, "tanh", "bf16", feat_p, None, am_p, None)
+    assert float((feat_p - feat).abs().max()) <= 1e-5 * float(feat.abs().max())      # equal up to the 4 index bits in the key
+    pts = x.reshape(B, N, C)
+    a0 = pts.gather(1, am.cpu().long()[:, :, None].expand(-1, -1, C))
+    a1 = pts[:, perm].gather(1, am_p.cpu().long()[:, :, None].expand(-1, -1, C))
+    assert float(((a0 - a1).abs().amax(dim=-1) > 0).float().mean()) < 0.02                # same winning POINT (near-ties aside)
+    # (3) batch independence: the first 37 clouds alone
+    feat_s = torch.empty(37, 512, device=DEV)
+    am_s = torch.empty(37, 512, device=DEV, dtype=torch.int32)
+    ops.pointnet_encode_forward(xd[:37], N, C, enc, "tanh", "bf16", feat_s, None, am_s, None)
+    assert torch.equal(feat_s, feat[:37]) and torch.equal(am_s, am[:37])
+
+
+def test_empty_batch_is_rejected():
+    from partmanip_b200.algorithms.algo_utils.network import PointNet
+    net = PointNet(3072, 10, dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False), 0).to(DEV)
+    with pytest.raises(ValueError, match="empty batch"):
+        net(torch.empty(0, 3072, device=DEV))
