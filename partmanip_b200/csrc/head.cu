@@ -116,7 +116,7 @@ struct BwdS {
 };
 
 template <int ACT>
-__global__ void __launch_bounds__(HT)
+__global__ void __launch_bounds__(HF)
 head_bwd_a_kernel(int B, int F, pm_head_params P, int out_dim, const float* __restrict__ h1, const float* __restrict__ h2,
                   const float* __restrict__ dout, int64_t lddo, float* __restrict__ dpre1, float* __restrict__ dfeat,
                   int64_t lddf, int dfeat_cols, float* __restrict__ part_all) {
@@ -124,48 +124,42 @@ head_bwd_a_kernel(int B, int F, pm_head_params P, int out_dim, const float* __re
   BwdS& S = *reinterpret_cast<BwdS*>(smem_raw);
   const int t = threadIdx.x, row0 = blockIdx.x * HR;
   float* part = part_all + (size_t)blockIdx.x * QPART;
-  for (int i = t; i < H2D * H1D; i += HT) S.W1s[i >> 7][i & 127] = P.W1[i];
-  for (int i = t; i < out_dim * H2D; i += HT) S.W2s[i >> 5][i & 31] = P.W2[i];
-  for (int i = t; i < HR * out_dim; i += HT) {
+  for (int i = t; i < H2D * H1D; i += HF) S.W1s[i >> 7][i & 127] = P.W1[i];
+  for (int i = t; i < out_dim * H2D; i += HF) S.W2s[i >> 5][i & 31] = P.W2[i];
+  for (int i = t; i < HR * out_dim; i += HF) {
     const int r = i / out_dim, o = i - r * out_dim;
     S.Ds[r][o] = (row0 + r < B) ? dout[(int64_t)(row0 + r) * lddo + o] : 0.f;
   }
-  for (int i = t; i < HR * H2D; i += HT) {
-    const int r = i >> 5, m = i & 31;
+  {
+    const int r = t >> 5, m = t & 31;                               // HR * H2D == HF
     S.H2s[r][m] = (row0 + r < B) ? h2[(int64_t)(row0 + r) * H2D + m] : 0.f;
   }
-  for (int i = t; i < HR * H1D; i += HT) {
+  for (int i = t; i < HR * H1D; i += HF) {
     const int r = i >> 7, nn = i & 127;
     S.H1s[r][nn] = (row0 + r < B) ? h1[(int64_t)(row0 + r) * H1D + nn] : 0.f;
   }
   __syncthreads();
-  // ---- dPre2[r][m] = (dout . W2)[r][m] * act'(h2)
+  // ---- dPre2[r][m] = (dout . W2)[r][m] * act'(h2): thread = (column m, row r)
   {
-    const int m = t & 31, rr = t >> 5;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int r = rr + 8 * q;
-      float a = 0.f;
-      for (int o = 0; o < out_dim; ++o) a = fmaf(S.Ds[r][o], S.W2s[o][m], a);
-      S.DP2s[r][m] = a * pm_act_bwd(ACT, S.H2s[r][m]);
-    }
+    const int m = t & 31, r = t >> 5;
+    float a = 0.f;
+    for (int o = 0; o < out_dim; ++o) a = fmaf(S.Ds[r][o], S.W2s[o][m], a);
+    S.DP2s[r][m] = a * pm_act_bwd(ACT, S.H2s[r][m]);
   }
   __syncthreads();
-  // ---- dPre1[r][n] = (dPre2 . W1)[r][n] * act'(h1)
+  // ---- dPre1[r][n] = (dPre2 . W1)[r][n] * act'(h1): thread = (column n, 4-row group rg)
   {
     const int n = t & 127, rg = t >> 7;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int m = 0; m < H2D; ++m) {
       const float w = S.W1s[m][n];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(S.DP2s[rg * 8 + i][m], w, acc[i]);
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(S.DP2s[rg * 4 + i][m], w, acc[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rg * 8 + i;
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
       const float v = acc[i] * pm_act_bwd(ACT, S.H1s[r][n]);
       S.DP1t[n][r] = v;
       if (row0 + r < B) dpre1[(int64_t)(row0 + r) * H1D + n] = v;
@@ -174,18 +168,18 @@ head_bwd_a_kernel(int B, int F, pm_head_params P, int out_dim, const float* __re
   __syncthreads();
   // ---- small gradients of this 16-row block
   {
-    const int n = t & 127, mg = t >> 7;          // dW1[m][n], m in [mg*16, +16)
-    float acc[16];
+    const int n = t & 127, mg = t >> 7;          // dW1[m][n], m in [mg*8, +8)
+    float acc[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll 4
     for (int r = 0; r < HR; ++r) {
       const float hv = S.H1s[r][n];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaf(S.DP2s[r][mg * 16 + i], hv, acc[i]);
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(S.DP2s[r][mg * 8 + i], hv, acc[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) part[QW1 + (mg * 16 + i) * H1D + n] = acc[i];
+    for (int i = 0; i < 8; ++i) part[QW1 + (mg * 8 + i) * H1D + n] = acc[i];
     if (t < H1D) {
       float s = 0.f;
 #pragma unroll
@@ -204,7 +198,7 @@ head_bwd_a_kernel(int B, int F, pm_head_params P, int out_dim, const float* __re
         for (int r = 0; r < HR; ++r) s += S.Ds[r][o];
       part[QB2 + o] = s;
     }
-    for (int i = t; i < out_dim * H2D; i += HT) {
+    for (int i = t; i < out_dim * H2D; i += HF) {
       const int o = i >> 5, m = i & 31;
       float s = 0.f;
 #pragma unroll
@@ -214,11 +208,11 @@ head_bwd_a_kernel(int B, int F, pm_head_params P, int out_dim, const float* __re
   }
   // ---- dfeat[r][k] = sum_n dPre1[r][n] W0[n][k]   (only the first dfeat_cols columns are consumed: max[,mean] part)
   if (dfeat) {
-    for (int k = t; k < dfeat_cols; k += HT) {
+    for (int k = t; k < dfeat_cols; k += HF) {
       float acc[HR];
 #pragma unroll
       for (int i = 0; i < HR; ++i) acc[i] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
       for (int n = 0; n < H1D; ++n) {
         const float w = __ldg(P.W0 + (int64_t)n * F + k);
         const float4 d0 = *reinterpret_cast<const float4*>(&S.DP1t[n][0]);
@@ -370,7 +364,7 @@ int pm_pointnet_head_backward(const float* feat, int64_t ldf, int B, int F, cons
       if (e != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));                     \
       attr_set = true;                                                                                                   \
     }                                                                                                                    \
-    head_bwd_a_kernel<ACTV><<<w.nA, HT, sizeof(BwdS), st>>>(B, F, *p, out_dim, h1, h2, dout, lddo, w.dpre1, dfeat, lddf,  \
+    head_bwd_a_kernel<ACTV><<<w.nA, HF, sizeof(BwdS), st>>>(B, F, *p, out_dim, h1, h2, dout, lddo, w.dpre1, dfeat, lddf,  \
                                                             dfeat_cols, w.partA);                                        \
   } break;
   switch (act) {
