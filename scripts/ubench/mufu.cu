@@ -14,6 +14,8 @@ __global__ void k(float* out, int iters) {
       if (OP == 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
       if (OP == 3) { unsigned r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(r) : "f"(v[i])); v[i] = __uint_as_float(r); }
       if (OP == 4) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(v[i]));
+      if (OP == 5) { unsigned r = __float_as_uint(v[i]); asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(r)); v[i] = __uint_as_float(r); }
+      if (OP == 6) { unsigned r = __float_as_uint(v[i]); asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(r)); v[i] = __uint_as_float(r); }
     }
   }
   long long t1 = clock64();
@@ -23,9 +25,9 @@ __global__ void k(float* out, int iters) {
 }
 int main() {
   float* d; cudaMalloc(&d, 1 << 20);
-  const char* names[] = {"MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "F2FP.BF16x2", "FFMA"};
+  const char* names[] = {"MUFU.TANH", "MUFU.EX2", "MUFU.RCP", "F2FP.BF16x2", "FFMA", "TANH.BF16x2 (instr)", "TANH.F16x2 (instr)"};
   for (int warps = 4; warps <= 16; warps *= 2)
-    for (int op = 0; op < 5; ++op) {
+    for (int op = 0; op < 7; ++op) {
       int iters = 2000;
       float h;
       for (int rep = 0; rep < 2; ++rep) {
@@ -34,6 +36,8 @@ int main() {
         if (op == 2) k<2><<<148, warps * 32>>>(d, iters);
         if (op == 3) k<3><<<148, warps * 32>>>(d, iters);
         if (op == 4) k<4><<<148, warps * 32>>>(d, iters);
+        if (op == 5) k<5><<<148, warps * 32>>>(d, iters);
+        if (op == 6) k<6><<<148, warps * 32>>>(d, iters);
         cudaDeviceSynchronize();
       }
       cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost);
