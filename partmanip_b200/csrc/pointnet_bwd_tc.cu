@@ -28,7 +28,8 @@ using namespace pmtc;
 constexpr int BT_THREADS = 256;          // 8 warps, thread = (row, column half); thread 0 also issues the MMAs (256 threads => 255 regs).
 // Measured alternatives (scripts/bwd_timing.py): 16 compute warps + an MMA warp (96-register cap) spills the dW3
 // accumulators to local memory and runs 30 % slower; a dedicated issuer warp does not help either, because the M3/M2 operand
-// streams (8 KB of SMEM per 64-cycle MMA) saturate shared memory and the column sums that run beside them slow down equally.
+// streams (8 KB of SMEM per 64-cycle MMA) saturate shared memory and the column sums that run beside them slow down equally;
+// M2 as 8 N=256 MMAs (dW2 transposed, both operands MN-major) is correct but slower too (0.468 vs 0.427 ms).
 constexpr int NCB = 8;                   // channel blocks of 64
 constexpr uint32_t KB16 = 16384;         // one 64-wide k-block of a 128-row operand
 constexpr uint32_t KB32 = 32768;         // one 64-wide k-block of a 256-row operand
