@@ -35,7 +35,7 @@ def ppo_cfg(E, device, precision):
         n_minibatches=8, device=device, eval_round=1, eval_frequence=10 ** 9, save_frequence=10 ** 9,
         test_only=False, save_pose=False, save_video=False, lr_schedule="fixed", lr=5e-5, desired_kl=0.1,
         epsilon_clip=0.2, gamma=0.99, lam=0.95, sampler="sequential", resume=None,
-        cuda_graph=os.environ.get("PM_CUDA_GRAPH", "1") == "1", cuda_graph_multi_rank=os.environ.get("PM_CUDA_GRAPH_MULTI", "0") == "1",
+        cuda_graph=os.environ.get("PM_CUDA_GRAPH", "1") == "1", cuda_graph_multi_rank=os.environ.get("PM_CUDA_GRAPH_MULTI", "1") == "1",
         tricks=dict(mini_adv_norm=False, whole_adv_norm=False, use_state_norm=True, use_clipped_value_loss=False,
                     use_grad_clip=True, max_grad_norm=0.5),
         model=dict(action_std=0.5, action_activate="tanh", clipAction=1.0,
@@ -318,9 +318,11 @@ def main():
     # ---- end-to-end arm: host-resident observations, H2D copy of every step's obs + D2H of the actions inside the timed region
     e2e = None
     if not args.no_e2e:
+        runner.release_graph()
         del runner, env
         torch.cuda.empty_cache()
         env_h, runner_h = make(host=True)
+        runner = runner_h
         e2e_warm = 2                                   # eager + graph-capture iterations stay outside the timed region
         ms_e2e, _, _ = timed(runner_h, env_h, max(2, args.steps // 2), e2e_warm, False)
         iters_run = max(2, args.steps // 2) + e2e_warm
@@ -350,7 +352,11 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing NCCL down: captured graphs hold NCCL work objects and destroy_process_group() can block on them
+        runner.release_graph()
+        barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -174,9 +174,10 @@ class ppo:
         # build extension: replay the whole device-side update (160 minibatch steps at E=4096) as ONE CUDA graph.  Legal
         # because the update has no host round trip (device-side KL-skip / step counters / loss sums) and sequential
         # minibatches are fixed slices of persistent buffers.  First call runs eagerly (allocates workspaces), the second
-        # captures, later ones replay.  Off for the random sampler (host-side permutation) and, by default, multi-rank.
+        # captures, later ones replay.  Off for the random sampler (host-side permutation).  Multi-rank: the NCCL all-reduces
+        # are captured too (thread_local capture mode); call release_graph() before destroying the process group.
         self.cuda_graph = bool(cfg.get('cuda_graph', True)) and cfg['sampler'] == 'sequential' and \
-            (self.world == 1 or bool(cfg.get('cuda_graph_multi_rank', False)))
+            (self.world == 1 or bool(cfg.get('cuda_graph_multi_rank', True)))
         self._graph, self._graph_calls, self._n_critic = None, 0, 0
         self.resume(cfg['resume'])
 
@@ -362,6 +363,13 @@ class ppo:
             ops.gather_rows(v, indices, out[k])
         return out
 
+    def release_graph(self):
+        """Drop the captured update graph (it pins NCCL work objects: do this before dist.destroy_process_group())."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._graph_calls = 0
+
     def _update_body(self):
         """The device-side part of update(): both phases over all epochs and minibatches (graph-capturable)."""
         ac = self.actor_critic
@@ -426,7 +434,8 @@ class ppo:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
-            with torch.cuda.graph(graph):
+            # thread_local: NCCL's watchdog thread polls CUDA events while this thread captures (multi-rank)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 self._update_body()
             self._graph, self._graph_launches = graph, ops.launch_count() - n0
             graph.replay()
