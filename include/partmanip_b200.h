@@ -176,6 +176,8 @@ int pm_linear_backward(const float* x, int64_t ldx, const float* W, const float*
  * h2[B,32] are kept for the backward), three launches backward.  out <= 32.  fp32.
  * dfeat (may be NULL) receives d/d(feat) for the first dfeat_cols columns (the pooled part; the proprio
  * tail is an input).  Gradients are OVERWRITTEN.
+ * PM_PREC_BF16: the three products with the F-wide dimension (feat.W0^T, dPre1.W0, dPre1^T.feat) and the 128->32 layer
+ * run as tcgen05 MMAs with bf16 operands / fp32 accumulation (1e-2 gate); PM_PREC_FP32: FFMA kernels (1e-4 gate).
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const float *W0, *b0; /* (128,F),(128)    final_mlp.0 */
@@ -186,10 +188,10 @@ typedef struct {
   float *W0, *b0, *W1, *b1, *W2, *b2;
 } pm_head_grads;
 int pm_pointnet_head_forward(const float* feat, int64_t ldf, int B, int F, const pm_head_params* p, int out_dim,
-                             int act, float* h1, float* h2, float* out, int64_t ldo, pm_stream_t s);
+                             int act, int precision, float* h1, float* h2, float* out, int64_t ldo, pm_stream_t s);
 size_t pm_pointnet_head_backward_ws_bytes(int B, int F);
 int pm_pointnet_head_backward(const float* feat, int64_t ldf, int B, int F, const pm_head_params* p, int out_dim,
-                              int act, const float* h1, const float* h2, const float* dout, int64_t lddo,
+                              int act, int precision, const float* h1, const float* h2, const float* dout, int64_t lddo,
                               const pm_head_grads* g, float* dfeat, int64_t lddf, int dfeat_cols, void* ws,
                               size_t ws_bytes, pm_stream_t s);
 

@@ -52,9 +52,9 @@ SIGNATURES = {
     "pm_linear_forward": (I, [P, L, P, P, P, L, I, I, I, I, P, P]),
     "pm_linear_backward_ws_bytes": (SZ, [I, I, I]),
     "pm_linear_backward": (I, [P, L, P, P, L, P, P, P, L, I, I, I, I, P, P, P]),
-    "pm_pointnet_head_forward": (I, [P, L, I, I, EP, I, I, P, P, P, L, P]),
+    "pm_pointnet_head_forward": (I, [P, L, I, I, EP, I, I, I, P, P, P, L, P]),
     "pm_pointnet_head_backward_ws_bytes": (SZ, [I, I]),
-    "pm_pointnet_head_backward": (I, [P, L, I, I, EP, I, I, P, P, P, L, EP, P, L, I, P, SZ, P]),
+    "pm_pointnet_head_backward": (I, [P, L, I, I, EP, I, I, I, P, P, P, L, EP, P, L, I, P, SZ, P]),
     "pm_pointnet_center": (I, [P, L, I, I, I, P]),
     "pm_pointnet_encode_forward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, P, SZ, P]),
     "pm_pointnet_encode_forward_ws_bytes": (SZ, [I, I, I, I]),

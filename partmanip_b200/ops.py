@@ -272,19 +272,20 @@ def linear_backward(x: Tensor, W: Tensor, dpre: Tensor, dW: Tensor, db: Optional
 
 # ------------------------------------------------------------------------------------------- K3b fused head
 def pointnet_head_forward(feat: Tensor, head_params: Sequence[Tensor], out_dim: int, act, h1: Tensor, h2: Tensor,
-                          out: Tensor) -> Tensor:
+                          out: Tensor, precision: str = "fp32") -> Tensor:
     """network.py:152-159: out = L2(act(L1(act(L0(feat))))); h1 (B,128) / h2 (B,32) are saved for the backward."""
     B, F, ldf = _rows(_f32(feat, "feat"), "feat")
     _, _, ldo = _rows(_f32(out, "out"), "out")
     assert h1.shape == (B, 128) and h2.shape == (B, 32) and h1.is_contiguous() and h2.is_contiguous()
     ps = _enc_struct(head_params)
-    check(lib.pm_pointnet_head_forward(_p(feat), ldf, B, F, ct.byref(ps), int(out_dim), PM_ACT[act], _p(h1), _p(h2), _p(out),
-                                       ldo, _stream()), "pm_pointnet_head_forward")
+    check(lib.pm_pointnet_head_forward(_p(feat), ldf, B, F, ct.byref(ps), int(out_dim), PM_ACT[act], PM_PREC[precision], _p(h1),
+                                       _p(h2), _p(out), ldo, _stream()), "pm_pointnet_head_forward")
     return out
 
 
 def pointnet_head_backward(feat: Tensor, head_params: Sequence[Tensor], out_dim: int, act, h1: Tensor, h2: Tensor,
-                           dout: Tensor, head_grads: Sequence[Tensor], dfeat: Optional[Tensor], dfeat_cols: int = 0):
+                           dout: Tensor, head_grads: Sequence[Tensor], dfeat: Optional[Tensor], dfeat_cols: int = 0,
+                           precision: str = "fp32"):
     """autograd of network.py:152-159 w.r.t. the six head tensors (+ d/d feat[:, :dfeat_cols])."""
     B, F, ldf = _rows(_f32(feat, "feat"), "feat")
     _, _, lddo = _rows(_f32(dout, "dout"), "dout")
@@ -294,7 +295,7 @@ def pointnet_head_backward(feat: Tensor, head_params: Sequence[Tensor], out_dim:
     nbytes = lib.pm_pointnet_head_backward_ws_bytes(B, F)
     ws = scratch(nbytes, feat.device, "headbwd")
     ps, gs = _enc_struct(head_params), _enc_struct(head_grads)
-    check(lib.pm_pointnet_head_backward(_p(feat), ldf, B, F, ct.byref(ps), int(out_dim), PM_ACT[act], _p(h1), _p(h2),
+    check(lib.pm_pointnet_head_backward(_p(feat), ldf, B, F, ct.byref(ps), int(out_dim), PM_ACT[act], PM_PREC[precision], _p(h1), _p(h2),
                                         _p(dout), lddo, ct.byref(gs), _p(dfeat), lddf, int(dfeat_cols), _p(ws), nbytes,
                                         _stream()), "pm_pointnet_head_backward")
 
