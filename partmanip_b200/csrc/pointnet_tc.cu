@@ -7,14 +7,19 @@
 // HALF of W3 (its 256 output channels, 128 KB) and half of W2 (128 channels, 32 KB); the hardware shares the
 // per-CTA operand halves, so nothing is replicated and nothing is re-read from L2/HBM after the prologue.
 //
-// Per tile of 256 points (128 per CTA):
-//   L1  CUDA cores : h1 = act(W1 x + b1)  (K = C <= 4: not a GEMM)       -> smem, bf16, 128B-swizzled K-major (A operand)
-//   L2  tcgen05    : D2[256 pts x 256 ch] = H1 . W2^T   (M=256 N=256 K=128, 8 MMAs)   acc in TMEM cols [0,256)
-//   E2  4 warps    : tcgen05.ld -> +b2 -> act -> bf16 -> smem H2 [128 pts x 256] (B operand of L3; overlays H1)
-//   L3  tcgen05    : D3^T[256 ch x 128 pts] = W3 . H2^T for (2 channel chunks) x (2 point halves), 16 MMAs each,
-//                    double-buffered in TMEM cols [256,384) / [384,512)
-//   E3  4 warps    : lane = channel, columns = points: running max (+ first-index argmax) entirely in registers —
-//                    the transposed orientation makes the symmetric max-pool a per-thread reduction, no shuffles.
+// Per tile of 256 points (128 per CTA); 17 warps = 4 epilogue groups of 4 warps (one warp of each group per scheduler) + 1
+// MMA-issue warp; every MMA is M=256 (pair), N=256, K=16:
+//   L1  groups A0,A1 : h1 = act(W1 x + b1)  (K = C <= 4: not a GEMM), 64 channels per group, computed into registers while the
+//                      previous tile's last MMAs run                          -> smem, bf16, 128B-swizzled K-major (A operand)
+//   L2  tcgen05      : D2[256 pts x 256 ch] = H1 . W2^T (8 MMAs)               -> TMEM region p (p = tile parity)
+//   E2  all 4 groups : tcgen05.ld -> +b2 -> act -> bf16 -> smem H2 [128 pts x 256] (B operand of L3; overlays H1).  Group g takes
+//                      the g-th 16-column slice of EVERY 64-channel k-block, so k-blocks complete in order and ...
+//   L3  tcgen05      : ... D3^T[256 ch x 256 pts] = W3 . H2^T of channel chunk 0 is issued k-block by k-block BEHIND E2 into
+//                      region p^1; chunk 1 follows into region p, which E2 has drained by then (16 MMAs each)
+//   E3  groups B0,B1 : lane = channel, columns = points (B0 columns [0,128), B1 [128,256)): the transposed orientation makes the
+//                      symmetric max-pool a per-thread FMNMX3 tree over TMEM columns; the argmax rides in the low 4 mantissa
+//                      bits of the compared value; the two column halves are merged once per cloud.
+// TMEM/b2/x loads are software-pipelined one step ahead.  Per-role clock64 stamps: make EXTRA=-DPM_TC_TIMING + scripts/tc_timing.py.
 // The (points x 128/256/512) activations never leave the SM; HBM sees 4C bytes per point in and 4 KB per cloud out.
 #include "tc_common.cuh"
 
