@@ -262,6 +262,18 @@ int pm_gather_rows(const float* src, int64_t lds, const int64_t* idx, float* out
 int pm_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n_rows, int width,
                  pm_stream_t s);
 
+/* ------------------------------------------------------------------------------------------
+ * NEXT ROW  depth -> world point cloud -> farthest-point subsample
+ * replaces utils/depth2tsdf.py:146-159 (back-projection, camera->world, workspace mask: points outside the open box
+ * (origin, origin+size) become (0,0,0)) and :160 (pytorch3d.ops.sample_farthest_points, start index 0, first index on ties).
+ * cam_intr (3x3) and vol_origin (3) are HOST arrays; cam_pose is a device (M,4,4) row-major array.
+ * ------------------------------------------------------------------------------------------ */
+int pm_depth2pc_backproject(const float* depth, int E, int M, int H, int W, const float* cam_intr, const float* cam_pose_dev,
+                            const float* vol_origin, float size, float* out /* (E, M*H*W, 3) */, pm_stream_t s);
+size_t pm_fps_ws_bytes(int E, int P);
+int pm_farthest_point_sample(const float* points /* (E,P,3) */, int E, int P, int K, float* out /* (E,K,3) */,
+                             int64_t* out_idx /* (E,K) or NULL */, void* ws, size_t ws_bytes, pm_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -399,3 +399,29 @@ def copy_rows(src: Tensor, dst: Tensor) -> Tensor:
     assert (n, w) == (n2, w2)
     check(lib.pm_copy_rows(_p(src), lds, _p(dst), ldd, n, w, _stream()), "pm_copy_rows")
     return dst
+
+
+# ------------------------------------------------------------------------------------------- next row: depth -> point cloud
+def depth2pc_backproject(depth: Tensor, cam_intr, cam_pose: Tensor, vol_origin, size: float, out: Optional[Tensor] = None) -> Tensor:
+    """utils/depth2tsdf.py:146-159.  depth (E,M,H,W) fp32 CUDA, cam_pose (M,4,4) fp32 CUDA -> masked world cloud (E, M*H*W, 3)."""
+    E, M, H, W = depth.shape
+    assert _f32(depth, "depth").is_contiguous() and _f32(cam_pose, "cam_pose").is_contiguous() and cam_pose.shape == (M, 4, 4)
+    if out is None:
+        out = torch.empty(E, M * H * W, 3, device=depth.device, dtype=torch.float32)
+    intr = (ct.c_float * 9)(*[float(v) for row in cam_intr for v in row])
+    org = (ct.c_float * 3)(*[float(v) for v in vol_origin])
+    check(lib.pm_depth2pc_backproject(_p(depth), E, M, H, W, intr, _p(cam_pose), org, float(size), _p(out), _stream()),
+          "pm_depth2pc_backproject")
+    return out
+
+
+def farthest_point_sample(points: Tensor, K: int, return_idx: bool = False):
+    """pytorch3d.ops.sample_farthest_points(points, K=K) semantics (start index 0, first index on ties): (E,P,3) -> (E,K,3)."""
+    E, P, three = points.shape
+    assert three == 3 and _f32(points, "points").is_contiguous()
+    out = torch.empty(E, K, 3, device=points.device, dtype=torch.float32)
+    idx = torch.empty(E, K, device=points.device, dtype=torch.int64) if return_idx else None
+    nbytes = lib.pm_fps_ws_bytes(E, P)
+    ws = scratch(nbytes, points.device, "fps")
+    check(lib.pm_farthest_point_sample(_p(points), E, P, int(K), _p(out), _p(idx), _p(ws), nbytes, _stream()), "pm_farthest_point_sample")
+    return (out, idx) if return_idx else out

@@ -1,0 +1,36 @@
+"""`TSDFVolume` — the point-cloud half of the reference class (utils/depth2tsdf.py:6-66, 136-173): same constructor,
+`register_camera(cam_pose, cam_intr, im_h, im_w, num_env)` and `depth2pc(depth_im) -> (num_env, 1024, 3)`, with the
+back-projection / workspace mask and the farthest-point sampling (pytorch3d there) running in libpartmanip_b200.so.
+The TSDF-integration half (integrate / sparse_voxel / extract_point_cloud) is outside this row and not mirrored.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class TSDFVolume(object):
+    def __init__(self, device, size=0.5, resolution=50, _vol_origin=(-0.25, -0.25, -0.0503)):
+        if not str(device).startswith("cuda"):
+            raise RuntimeError("partmanip_b200 runs on CUDA devices only (no CPU fallback); got device=%r" % (device,))
+        self._size = size
+        self._resolution = resolution
+        self._voxel_size = self._size / self._resolution
+        self.device = device
+        self._vol_origin = [float(v) for v in _vol_origin]
+        self.num_points = 1024                                  # depth2tsdf.py:160 hard-codes K=1024
+
+    def register_camera(self, cam_pose, cam_intr, im_h, im_w, num_env):
+        """depth2tsdf.py:31-66 (the camera bookkeeping depth2pc needs)."""
+        cam_pose = np.asarray(cam_pose, dtype=np.float32)
+        self.registered_shape = (num_env, cam_pose.shape[0], im_h, im_w)
+        self.cam_pose = torch.tensor(cam_pose, device=self.device).float().contiguous()     # (m, 4, 4); identical for every env
+        self.cam_intr = np.asarray(cam_intr, dtype=np.float64)
+
+    def depth2pc(self, depth_im):
+        """depth2tsdf.py:136-173: depth_im (b, m, h, w) -> (b, 1024, 3)."""
+        assert tuple(depth_im.shape) == tuple(self.registered_shape)
+        cloud = ops.depth2pc_backproject(depth_im.float().contiguous(), self.cam_intr, self.cam_pose, self._vol_origin, self._size)
+        return ops.farthest_point_sample(cloud, self.num_points)
