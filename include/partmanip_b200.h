@@ -271,7 +271,9 @@ int pm_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t
 int pm_depth2pc_backproject(const float* depth, int E, int M, int H, int W, const float* cam_intr, const float* cam_pose_dev,
                             const float* vol_origin, float size, float* out /* (E, M*H*W, 3) */, pm_stream_t s);
 size_t pm_fps_ws_bytes(int E, int P);
-int pm_farthest_point_sample(const float* points /* (E,P,3) */, int E, int P, int K, float* out /* (E,K,3) */,
+/* compact != 0 (needs P % 4 == 0): the cloud is first compacted to its non-zero points + the first zero point (identical
+ * picks: the masked points are exact duplicates of (0,0,0)), so the K passes touch only the valid points. */
+int pm_farthest_point_sample(const float* points /* (E,P,3) */, int E, int P, int K, int compact, float* out /* (E,K,3) */,
                              int64_t* out_idx /* (E,K) or NULL */, void* ws, size_t ws_bytes, pm_stream_t s);
 
 #ifdef __cplusplus

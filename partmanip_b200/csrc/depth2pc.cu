@@ -151,6 +151,126 @@ fps_kernel(const float* __restrict__ pts /* (E,P,3) */, int P, int K, float* __r
   }
 }
 
+// ---- order-preserving compaction: keep every non-zero point and the FIRST zero point.  FPS is invariant under removing exact
+//      duplicates as long as first occurrences stay in order (a duplicate of a selected point has min-distance 0, a duplicate
+//      of an unselected one ties with it and the first index wins), and the masked points are all duplicates of (0,0,0).
+//      The compacted cloud is padded to a multiple of 4 with copies of its point 0 (never selected before a distinct point).
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_compact_kernel(const float* __restrict__ pts, int P, float* __restrict__ cp /* (E, P+4, 3) */, int32_t* __restrict__ om /* (E, P+4) */,
+                   int32_t* __restrict__ counts /* (E) */) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry, s_z0;
+  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = pts + (int64_t)e * P * 3;
+  float* c = cp + (int64_t)e * (P + 4) * 3;
+  int32_t* o = om + (int64_t)e * (P + 4);
+  if (tid == 0) { s_carry = 0; s_z0 = 0x7fffffff; }
+  __syncthreads();
+  int z0 = 0x7fffffff;
+  for (int i = tid; i < P; i += FPS_THREADS)
+    if (z0 == 0x7fffffff && p[(int64_t)i * 3] == 0.f && p[(int64_t)i * 3 + 1] == 0.f && p[(int64_t)i * 3 + 2] == 0.f) z0 = i;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) z0 = min(z0, __shfl_xor_sync(0xffffffffu, z0, s));
+  if (lane == 0 && z0 != 0x7fffffff) atomicMin(&s_z0, z0);
+  __syncthreads();
+  z0 = s_z0;
+  for (int base = 0; base < P; base += FPS_THREADS) {
+    const int i = base + tid;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool keep = false;
+    if (i < P) {
+      x = p[(int64_t)i * 3]; y = p[(int64_t)i * 3 + 1]; z = p[(int64_t)i * 3 + 2];
+      keep = (x != 0.f || y != 0.f || z != 0.f) || i == z0;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const int n = s_warp[w]; if (w < warp) woff += n; total += n; }
+    const int carry = s_carry;
+    if (keep) {
+      const int pos = carry + woff + __popc(mask & ((1u << lane) - 1u));
+      c[(int64_t)pos * 3] = x; c[(int64_t)pos * 3 + 1] = y; c[(int64_t)pos * 3 + 2] = z;
+      o[pos] = i;
+    }
+    __syncthreads();
+    if (tid == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int n = s_carry;
+    counts[e] = n;
+    while (n & 3) { c[(int64_t)n * 3] = c[0]; c[(int64_t)n * 3 + 1] = c[1]; c[(int64_t)n * 3 + 2] = c[2]; o[n] = o[0]; ++n; }
+  }
+}
+
+// FPS over the compacted clouds (per-cloud point count in device memory; min distances in shared memory when they fit)
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_compacted_kernel(const float* __restrict__ cp, const int32_t* __restrict__ om, const int32_t* __restrict__ counts, int P, int K,
+                     float* __restrict__ mind_g /* (E, P+4) */, float* __restrict__ out, int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) float mind_s[];
+  __shared__ float red_v[32];
+  __shared__ int red_i[32];
+  __shared__ int s_last;
+  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = cp + (int64_t)e * (P + 4) * 3;
+  const int32_t* o = om + (int64_t)e * (P + 4);
+  const int n4 = (counts[e] + 3) >> 2;                                  // groups of 4 points (padded)
+  float* mind = (n4 * 4 <= FPS_SMEM_POINTS) ? mind_s : mind_g + (int64_t)e * (P + 4);
+  for (int i = tid; i < n4 * 4; i += FPS_THREADS) mind[i] = 3.402823466e+38f;
+  int last = 0;
+  if (tid == 0) {
+    out[(int64_t)e * K * 3 + 0] = p[0]; out[(int64_t)e * K * 3 + 1] = p[1]; out[(int64_t)e * K * 3 + 2] = p[2];
+    if (out_idx) out_idx[(int64_t)e * K] = o[0];
+  }
+  __syncthreads();
+  for (int k = 1; k < K; ++k) {
+    const float lx = p[(int64_t)last * 3], ly = p[(int64_t)last * 3 + 1], lz = p[(int64_t)last * 3 + 2];
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    for (int g4 = tid; g4 < n4; g4 += FPS_THREADS) {
+      const float4 a = reinterpret_cast<const float4*>(p)[3 * g4], b = reinterpret_cast<const float4*>(p)[3 * g4 + 1],
+                   c = reinterpret_cast<const float4*>(p)[3 * g4 + 2];
+      float4 m4 = reinterpret_cast<float4*>(mind)[g4];
+      m4.x = fminf(m4.x, sqdist(a.x, a.y, a.z, lx, ly, lz));
+      m4.y = fminf(m4.y, sqdist(a.w, b.x, b.y, lx, ly, lz));
+      m4.z = fminf(m4.z, sqdist(b.z, b.w, c.x, lx, ly, lz));
+      m4.w = fminf(m4.w, sqdist(c.y, c.z, c.w, lx, ly, lz));
+      reinterpret_cast<float4*>(mind)[g4] = m4;
+      if (m4.x > bv) { bv = m4.x; bi = 4 * g4; }
+      if (m4.y > bv) { bv = m4.y; bi = 4 * g4 + 1; }
+      if (m4.z > bv) { bv = m4.z; bi = 4 * g4 + 2; }
+      if (m4.w > bv) { bv = m4.w; bi = 4 * g4 + 3; }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, s);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = red_v[lane]; bi = red_i[lane];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        if (bi == 0x7fffffff) bi = 0;
+        s_last = bi;
+        float* o3 = out + ((int64_t)e * K + k) * 3;
+        o3[0] = p[(int64_t)bi * 3]; o3[1] = p[(int64_t)bi * 3 + 1]; o3[2] = p[(int64_t)bi * 3 + 2];
+        if (out_idx) out_idx[(int64_t)e * K + k] = o[bi];
+      }
+    }
+    __syncthreads();
+    last = s_last;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,12 +295,35 @@ int pm_depth2pc_backproject(const float* depth, int E, int M, int H, int W, cons
   return PM_OK;
 }
 
-size_t pm_fps_ws_bytes(int E, int P) { return P > FPS_SMEM_POINTS ? (size_t)E * P * sizeof(float) : 256; }
+// workspace: [compacted points (E,P+4,3) | original indices (E,P+4) | counts (E) | min distances (E,P+4)]
+size_t pm_fps_ws_bytes(int E, int P) {
+  return pm_align_up((size_t)E * (P + 4) * 12, 256) + pm_align_up((size_t)E * (P + 4) * 4, 256) + pm_align_up((size_t)E * 4, 256) +
+         pm_align_up((size_t)E * (P + 4) * 4, 256);
+}
 
-int pm_farthest_point_sample(const float* points, int E, int P, int K, float* out, int64_t* out_idx, void* ws, size_t ws_bytes,
-                             pm_stream_t s) {
+int pm_farthest_point_sample(const float* points, int E, int P, int K, int compact, float* out, int64_t* out_idx, void* ws,
+                             size_t ws_bytes, pm_stream_t s) {
   PM_REQUIRE(points && out, PM_ERR_ARG, "pm_farthest_point_sample: null pointer");
   PM_REQUIRE(E > 0 && P > 0 && K > 0 && K <= P, PM_ERR_SHAPE, "pm_farthest_point_sample: E=%d P=%d K=%d (need K <= P)", E, P, K);
+  if (compact) {
+    PM_REQUIRE(ws && ws_bytes >= pm_fps_ws_bytes(E, P) && pm_aligned(ws, 256), PM_ERR_ARG, "pm_farthest_point_sample: workspace too small / unaligned");
+    char* base = reinterpret_cast<char*>(ws);
+    float* cp = reinterpret_cast<float*>(base);
+    int32_t* om = reinterpret_cast<int32_t*>(base + pm_align_up((size_t)E * (P + 4) * 12, 256));
+    int32_t* counts = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(om) + pm_align_up((size_t)E * (P + 4) * 4, 256));
+    float* mind = reinterpret_cast<float*>(reinterpret_cast<char*>(counts) + pm_align_up((size_t)E * 4, 256));
+    PM_REQUIRE(((size_t)(P + 4) * 12) % 16 == 0, PM_ERR_SHAPE, "pm_farthest_point_sample: compact path needs P %% 4 == 0 (P=%d)", P);
+    static bool attr_set_c = false;
+    if (!attr_set_c) {
+      cudaError_t e1 = cudaFuncSetAttribute(fps_compacted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FPS_SMEM_POINTS * 4);
+      if (e1 != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1));
+      attr_set_c = true;
+    }
+    fps_compact_kernel<<<E, FPS_THREADS, 0, pm_st(s)>>>(points, P, cp, om, counts);
+    fps_compacted_kernel<<<E, FPS_THREADS, FPS_SMEM_POINTS * 4, pm_st(s)>>>(cp, om, counts, P, K, mind, out, out_idx);
+    PM_CHECK_LAUNCH("pm_farthest_point_sample(compact)");
+    return PM_OK;
+  }
   const bool vec = (P % 4 == 0) && pm_aligned(points, 16);
   if (P <= FPS_SMEM_POINTS) {
     static bool attr_set = false;

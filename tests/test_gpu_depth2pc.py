@@ -52,3 +52,20 @@ def test_tsdfvolume_depth2pc_end_to_end():
         a = np.unique(np.round(out[e], 5), axis=0)
         b = np.unique(np.round(want[e], 5), axis=0)
         assert a.shape == b.shape and float(np.abs(a - b).max()) <= 2e-5
+
+
+@pytest.mark.parametrize("zero_frac", [0.0, 0.5, 0.97, 1.0])
+def test_fps_compacted_equals_plain(zero_frac):
+    """Compacting to the non-zero points + the first zero point leaves the picks unchanged (same coordinates AND the same
+    original indices), also when fewer distinct points than K remain (repeats of point 0)."""
+    from partmanip_b200 import ops
+    rng = np.random.default_rng(int(zero_frac * 100))
+    E, P, K = 3, 4096, 256
+    pts = rng.uniform(-1, 1, (E, P, 3)).astype(np.float32)
+    pts[rng.uniform(size=(E, P)) < zero_frac] = 0.0
+    d = torch.from_numpy(pts).to(DEV)
+    a, ia = ops.farthest_point_sample(d, K, return_idx=True, compact=False)
+    b, ib = ops.farthest_point_sample(d, K, return_idx=True, compact=True)
+    assert torch.equal(a, b) and torch.equal(ia, ib)
+    want_pts, want_idx = D.farthest_point_sample(pts, K)
+    assert np.array_equal(ib.cpu().numpy(), want_idx)
