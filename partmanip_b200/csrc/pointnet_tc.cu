@@ -253,7 +253,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       uint32_t h1[32];
       if (grp == 0) layer1_part<ACT, 0, 8>(xv, sW1, sB1, h1); else layer1_part<ACT, 8, 16>(xv, sW1, sB1, h1);
       if (tid == 0) TSTAMP(1);
-      // the H region is still being read by the previous tile's layer-3 MMAs
+      // k-blocks 0-1 of H (= H1) are still being read by the first half of the previous tile's last layer-3 group
       if (it > 0) ok = mbar_wait(bar(BAR_L3_DONE), (it - 1) & 1, err, 101);
       if (!ok) break;
       if (tid == 0) TSTAMP(2);
@@ -413,9 +413,14 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
       // ---- group 1 (channel chunk 1) into region p: E2 is done with the layer-2 accumulator (all four k-blocks arrived)
       if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) l3_mma(1, colp, k, k > 0);
+        for (int k = 0; k < 16; ++k) {
+          l3_mma(1, colp, k, k > 0);
+          // the group walks K in order: after its 8th step nothing reads k-blocks 0-1 of H any more — exactly where the next
+          // tile's H1 lives — so the next tile's layer 1 can be stored (and its layer-2 MMAs queued right behind this group)
+          // about 1 k cycles before the group completes
+          if (k == 7) umma_commit_mc(bar(BAR_L3_DONE));
+        }
         umma_commit_mc(bar(BAR_G_FULL1));
-        umma_commit_mc(bar(BAR_L3_DONE));
       }
       __syncwarp();
       if (lane == 0) TSTAMP(32);
