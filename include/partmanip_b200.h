@@ -271,8 +271,11 @@ int pm_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t
 int pm_depth2pc_backproject(const float* depth, int E, int M, int H, int W, const float* cam_intr, const float* cam_pose_dev,
                             const float* vol_origin, float size, float* out /* (E, M*H*W, 3) */, pm_stream_t s);
 size_t pm_fps_ws_bytes(int E, int P);
+/* how many 8-CTA clusters (= clouds) of the cluster sampler the device keeps resident at once (cudaOccupancyMaxActiveClusters) */
+int pm_fps_cluster_max_active(void);
 /* compact != 0 (needs P % 4 == 0): the cloud is first compacted to its non-zero points + the first zero point (identical
- * picks: the masked points are exact duplicates of (0,0,0)), so the K passes touch only the valid points. */
+ * picks: the masked points are exact duplicates of (0,0,0)), so the K passes touch only the valid points.
+ * compact: 0 = none, 1 = auto (P > 48 Ki -> one 8-CTA cluster per cloud, else one CTA per cloud), 2 = cluster, 3 = one CTA. */
 int pm_farthest_point_sample(const float* points /* (E,P,3) */, int E, int P, int K, int compact, float* out /* (E,K,3) */,
                              int64_t* out_idx /* (E,K) or NULL */, void* ws, size_t ws_bytes, pm_stream_t s);
 

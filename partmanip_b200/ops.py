@@ -415,8 +415,10 @@ def depth2pc_backproject(depth: Tensor, cam_intr, cam_pose: Tensor, vol_origin, 
     return out
 
 
-def farthest_point_sample(points: Tensor, K: int, return_idx: bool = False, compact: Optional[bool] = None):
-    """pytorch3d.ops.sample_farthest_points(points, K=K) semantics (start index 0, first index on ties): (E,P,3) -> (E,K,3)."""
+def farthest_point_sample(points: Tensor, K: int, return_idx: bool = False, compact=None):
+    """pytorch3d.ops.sample_farthest_points(points, K=K) semantics (start index 0, first index on ties): (E,P,3) -> (E,K,3).
+
+    compact: None/True = auto, False = no compaction, 2 = force the 8-CTA cluster kernel, 3 = force one CTA per cloud."""
     E, P, three = points.shape
     assert three == 3 and _f32(points, "points").is_contiguous()
     out = torch.empty(E, K, 3, device=points.device, dtype=torch.float32)
@@ -425,6 +427,6 @@ def farthest_point_sample(points: Tensor, K: int, return_idx: bool = False, comp
         compact = P % 4 == 0          # identical picks, K passes over the valid points only
     nbytes = lib.pm_fps_ws_bytes(E, P)
     ws = scratch(nbytes, points.device, "fps")
-    check(lib.pm_farthest_point_sample(_p(points), E, P, int(K), int(bool(compact)), _p(out), _p(idx), _p(ws), nbytes, _stream()),
+    check(lib.pm_farthest_point_sample(_p(points), E, P, int(K), int(compact), _p(out), _p(idx), _p(ws), nbytes, _stream()),
           "pm_farthest_point_sample")
     return (out, idx) if return_idx else out

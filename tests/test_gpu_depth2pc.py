@@ -69,3 +69,72 @@ def test_fps_compacted_equals_plain(zero_frac):
     assert torch.equal(a, b) and torch.equal(ia, ib)
     want_pts, want_idx = D.farthest_point_sample(pts, K)
     assert np.array_equal(ib.cpu().numpy(), want_idx)
+
+
+@pytest.mark.parametrize("E,P,K,zero_frac", [(3, 4096, 256, 0.5),       # small slices (64 groups per CTA)
+                                             (2, 40, 8, 0.0),            # fewer groups than CTAs x threads: idle CTAs / threads
+                                             (1, 4, 4, 1.0),             # one distinct point: repeats of point 0
+                                             (2, 200000, 48, 0.0),       # slices cross the shared-memory / L2 boundary (18 432 points)
+                                             (1, 300000, 24, 0.0),       # more than 32 Ki points per CTA (min distances in the global scratch)
+                                             (1, 600000, 8, 0.0),        # more than 64 Ki points per CTA (pruned kernel: unsummarised, streamed blocks)
+                                             (2, 65536, 1024, 0.9)])
+@pytest.mark.parametrize("mode", [2, 4])
+def test_fps_cluster_kernel_bit_exact(E, P, K, zero_frac, mode):
+    """The 8-CTA cluster kernels (registers + DSMEM candidate exchange; mode 4 = with exact bounding-box pruning) make the
+    oracle's picks, index for index."""
+    from partmanip_b200 import ops
+    rng = np.random.default_rng(P + K)
+    pts = rng.uniform(-1, 1, (E, P, 3)).astype(np.float32)
+    pts[rng.uniform(size=(E, P)) < zero_frac] = 0.0
+    d = torch.from_numpy(pts).to(DEV)
+    got, idx = ops.farthest_point_sample(d, K, return_idx=True, compact=mode)
+    want_pts, want_idx = D.farthest_point_sample(pts, K)
+    assert np.array_equal(idx.cpu().numpy(), want_idx)
+    assert np.array_equal(got.cpu().numpy(), want_pts)
+
+
+def test_fps_cluster_equals_one_cta_per_cloud_with_ties():
+    """Quantised coordinates produce many exactly tied distances: the first index must win in every reduction stage
+    (thread, warp, CTA, cluster) exactly as in the one-CTA kernel."""
+    from partmanip_b200 import ops
+    rng = np.random.default_rng(7)
+    pts = (rng.integers(-8, 9, (20, 60000, 3)) / 8.0).astype(np.float32)
+    d = torch.from_numpy(pts).to(DEV)
+    a, ia = ops.farthest_point_sample(d, 200, return_idx=True, compact=3)
+    b, ib = ops.farthest_point_sample(d, 200, return_idx=True, compact=2)
+    c, ic = ops.farthest_point_sample(d, 200, return_idx=True, compact=False)
+    p, ip = ops.farthest_point_sample(d, 200, return_idx=True, compact=4)
+    assert torch.equal(ia, ib) and torch.equal(a, b) and torch.equal(ia, ic)
+    assert torch.equal(ia, ip) and torch.equal(a, p)
+
+
+def _smooth_scene_depth(E, M, H, W, seed):
+    """Depth images of a smooth scene (tilted plane + bumps + a box): neighbouring pixels are neighbouring points."""
+    g = torch.Generator().manual_seed(seed)
+    v, u = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+    ph = torch.rand(E, M, 4, generator=g) * 6.28
+    d = 0.55 + 0.1 * u + 0.05 * v + 0.03 * torch.sin(5 * u + ph[..., 0, None, None]) * torch.cos(4 * v + ph[..., 1, None, None])
+    box = ((u - 0.2 * torch.cos(ph[..., 2, None, None])).abs() < 0.25) & ((v - 0.2 * torch.sin(ph[..., 3, None, None])).abs() < 0.2)
+    return torch.where(box, d - 0.12, d).float().contiguous()
+
+
+def test_fps_pruned_on_depth_image_clouds():
+    """Spatially coherent clouds (what depth2pc produces) are where the pruning skips almost everything: the picks must still
+    be the one-CTA kernel's and the oracle's."""
+    from partmanip_b200 import ops
+    E, M, H, W = 3, 3, 288, 512
+    depth = _smooth_scene_depth(E, M, H, W, 5).to(DEV)
+    intr = np.array([[366.0, 0, W // 2], [0, 366.0, H // 2], [0, 0, 1]])
+    pose = torch.eye(4, device=DEV).repeat(M, 1, 1).contiguous()
+    pose[:, 2, 3] = -0.3
+    pose[1, 0, 3] = 0.05
+    pose[2, 1, 3] = -0.05
+    cloud = ops.depth2pc_backproject(depth, intr, pose, [-0.25, -0.25, -0.0503], 0.5)
+    valid = float((cloud.abs().sum(-1) > 0).float().mean())
+    assert 0.05 < valid < 0.95
+    a, ia = ops.farthest_point_sample(cloud, 1024, return_idx=True, compact=3)
+    b, ib = ops.farthest_point_sample(cloud, 1024, return_idx=True, compact=4)
+    c, ic = ops.farthest_point_sample(cloud, 1024, return_idx=True)          # auto -> pruned cluster at this size
+    assert torch.equal(ia, ib) and torch.equal(a, b) and torch.equal(ia, ic)
+    want_pts, want_idx = D.farthest_point_sample(cloud[:1].cpu().numpy(), 1024)
+    assert np.array_equal(ib[:1].cpu().numpy(), want_idx) and np.array_equal(b[:1].cpu().numpy(), want_pts)
