@@ -270,6 +270,12 @@ int pm_copy_rows(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t
  * ------------------------------------------------------------------------------------------ */
 int pm_depth2pc_backproject(const float* depth, int E, int M, int H, int W, const float* cam_intr, const float* cam_pose_dev,
                             const float* vol_origin, float size, float* out /* (E, M*H*W, 3) */, pm_stream_t s);
+/* The same, reading the E*M camera images in place through a device table of pointers (view index = e*M + m), with the stacking
+ * step of tasks/hand_base.py:317-324 folded in: d = -image when negate != 0, then +-inf -> inf_value (100 there).  aligned16 = every
+ * image pointer is 16-byte aligned (enables 16-byte loads). */
+int pm_depth2pc_backproject_views(const float* const* depth_views_dev, int E, int M, int H, int W, int aligned16, int negate,
+                                  float inf_value, const float* cam_intr, const float* cam_pose_dev, const float* vol_origin, float size,
+                                  float* out /* (E, M*H*W, 3) */, pm_stream_t s);
 size_t pm_fps_ws_bytes(int E, int P);
 /* how many 8-CTA clusters (= clouds) of the cluster sampler the device keeps resident at once (cudaOccupancyMaxActiveClusters) */
 int pm_fps_cluster_max_active(void);

@@ -23,6 +23,13 @@ def pixel_maps(im_h: int, im_w: int):
     return xmap, ymap
 
 
+def stack_views(camera_tensor_list) -> np.ndarray:
+    """tasks/hand_base.py:317-324: per-env lists of per-view (H, W) depth images -> (E, M, H, W), negated, +-inf -> 100."""
+    d = np.stack([np.stack([np.asarray(v, np.float32) for v in views], axis=0) for views in camera_tensor_list], axis=0)
+    d = -d
+    return np.where(np.isinf(d), np.float32(100), d).astype(np.float32)
+
+
 def backproject(depth: np.ndarray, cam_intr: np.ndarray, cam_pose: np.ndarray, vol_origin, size: float) -> np.ndarray:
     """depth (E, M, H, W) fp32, cam_intr (3,3), cam_pose (M,4,4) -> masked world cloud (E, M*H*W, 3): points outside the
     open box (origin, origin+size) are zeroed (depth2tsdf.py:146-159)."""

@@ -65,6 +65,7 @@ SIGNATURES = {
     "pm_adam_ws_bytes": (SZ, [L]),
     "pm_adam_step": (I, [P, P, P, P, L, L, F, F, F, F, P, P, P, P]),
     "pm_depth2pc_backproject": (I, [P, I, I, I, I, C.POINTER(F), P, C.POINTER(F), F, P, P]),
+    "pm_depth2pc_backproject_views": (I, [P, I, I, I, I, I, I, F, C.POINTER(F), P, C.POINTER(F), F, P, P]),
     "pm_fps_ws_bytes": (SZ, [I, I]),
     "pm_fps_cluster_max_active": (I, []),
     "pm_farthest_point_sample": (I, [P, I, I, I, I, P, P, P, SZ, P]),

@@ -73,6 +73,56 @@ backproject4_kernel(const float* __restrict__ depth, int E, int M, int HW, int W
   }
 }
 
+// The same back-projection reading the E*M camera images where the simulator left them (a device table of pointers), with the
+// reference's stacking step folded in: d = -image (negate), +-inf -> inf_value (tasks/hand_base.py:317-324).  The stacked
+// (E,M,H,W) tensor and the negated / isinf / where temporaries never exist.
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+backproject_views_kernel(const float* const* __restrict__ views /* E*M pointers to (H,W) images */, int E, int M, int HW, int W, int negate,
+                         float inf_value, float cx, float cy, float fx, float fy, const float* __restrict__ cam_pose, float ox, float oy,
+                         float oz, float size, float* __restrict__ out) {
+  constexpr int V = VEC4 ? 4 : 1;
+  const int64_t totalv = (int64_t)E * M * HW / V;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < totalv; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = q * V;
+    const int p0i = (int)(i0 % HW);
+    const int view = (int)(i0 / HW);
+    const int m = view % M;
+    const float* img = views[view];
+    float dd[V];
+    if (VEC4) {
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(img + p0i));
+      dd[0] = d4.x; dd[V > 1 ? 1 : 0] = d4.y; dd[V > 2 ? 2 : 0] = d4.z; dd[V > 3 ? 3 : 0] = d4.w;
+    } else {
+      dd[0] = __ldg(img + p0i);
+    }
+    const float* T = cam_pose + m * 16;
+    float o[3 * V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int p = p0i + j;
+      float d = negate ? -dd[j] : dd[j];
+      if (isinf(d)) d = inf_value;
+      const float col = (float)(p % W), row = (float)(p / W);
+      const float a0 = __fdiv_rn(__fmul_rn(col - cx, d), fx);
+      const float a1 = __fdiv_rn(__fmul_rn(row - cy, d), fy);
+      float w[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) w[a] = fmaf(d, T[a * 4 + 2], fmaf(a1, T[a * 4 + 1], a0 * T[a * 4 + 0])) + T[a * 4 + 3];
+      const bool valid = w[0] < size + ox && w[1] < size + oy && w[2] < size + oz && w[0] > ox && w[1] > oy && w[2] > oz;
+      o[3 * j] = valid ? w[0] : 0.f; o[3 * j + 1] = valid ? w[1] : 0.f; o[3 * j + 2] = valid ? w[2] : 0.f;
+    }
+    if (VEC4) {
+      float4* dst = reinterpret_cast<float4*>(out + i0 * 3);
+      dst[0] = make_float4(o[0], o[1], o[2], o[V > 1 ? 3 : 0]);
+      dst[1] = make_float4(o[V > 1 ? 4 : 0], o[V > 1 ? 5 : 0], o[V > 2 ? 6 : 0], o[V > 2 ? 7 : 0]);
+      dst[2] = make_float4(o[V > 2 ? 8 : 0], o[V > 3 ? 9 : 0], o[V > 3 ? 10 : 0], o[V > 3 ? 11 : 0]);
+    } else {
+      out[i0 * 3] = o[0]; out[i0 * 3 + 1] = o[1]; out[i0 * 3 + 2] = o[2];
+    }
+  }
+}
+
 constexpr int FPS_THREADS = 1024;
 constexpr int FPS_SMEM_POINTS = 48 * 1024;   // running min-distances kept in shared memory up to this many points (192 KB)
 
@@ -721,6 +771,27 @@ int pm_depth2pc_backproject(const float* depth, int E, int M, int H, int W, cons
                                                      cam_pose_dev, vol_origin[0], vol_origin[1], vol_origin[2], size, out);
   }
   PM_CHECK_LAUNCH("pm_depth2pc_backproject");
+  return PM_OK;
+}
+
+int pm_depth2pc_backproject_views(const float* const* depth_views_dev, int E, int M, int H, int W, int aligned16, int negate,
+                                  float inf_value, const float* cam_intr, const float* cam_pose_dev, const float* vol_origin, float size,
+                                  float* out, pm_stream_t s) {
+  PM_REQUIRE(depth_views_dev && cam_intr && cam_pose_dev && vol_origin && out, PM_ERR_ARG, "pm_depth2pc_backproject_views: null pointer");
+  PM_REQUIRE(E > 0 && M > 0 && H > 0 && W > 0, PM_ERR_SHAPE, "pm_depth2pc_backproject_views: E=%d M=%d H=%d W=%d", E, M, H, W);
+  const int64_t total = (int64_t)E * M * H * W;
+  const bool vec = aligned16 && (H * W) % 4 == 0 && pm_aligned(out, 16);
+  const int64_t work = vec ? total / 4 : total;
+  const int blocks = (int)((work + 255) / 256 < (int64_t)PM_NUM_SMS * 16 ? (work + 255) / 256 : (int64_t)PM_NUM_SMS * 16);
+  if (vec)
+    backproject_views_kernel<true><<<blocks, 256, 0, pm_st(s)>>>(depth_views_dev, E, M, H * W, W, negate, inf_value, cam_intr[2], cam_intr[5],
+                                                                 cam_intr[0], cam_intr[4], cam_pose_dev, vol_origin[0], vol_origin[1],
+                                                                 vol_origin[2], size, out);
+  else
+    backproject_views_kernel<false><<<blocks, 256, 0, pm_st(s)>>>(depth_views_dev, E, M, H * W, W, negate, inf_value, cam_intr[2], cam_intr[5],
+                                                                  cam_intr[0], cam_intr[4], cam_pose_dev, vol_origin[0], vol_origin[1],
+                                                                  vol_origin[2], size, out);
+  PM_CHECK_LAUNCH("pm_depth2pc_backproject_views");
   return PM_OK;
 }
 

@@ -415,10 +415,38 @@ def depth2pc_backproject(depth: Tensor, cam_intr, cam_pose: Tensor, vol_origin, 
     return out
 
 
+def view_pointer_table(camera_tensor_list) -> Tuple[Tensor, bool]:
+    """Device table of the E*M image pointers of `camera_tensor_list[env][view]` (each an (H,W) fp32 CUDA tensor, as Isaac Gym's
+    camera tensors are) + whether all of them are 16-byte aligned.  The simulator reuses the buffers, so build it once."""
+    ptrs = []
+    for views in camera_tensor_list:
+        for t in views:
+            assert _f32(t, "camera tensor").is_contiguous()
+            ptrs.append(t.data_ptr())
+    dev = camera_tensor_list[0][0].device
+    table = torch.tensor(ptrs, dtype=torch.int64).to(dev)
+    return table, all(p % 16 == 0 for p in ptrs)
+
+
+def depth2pc_backproject_views(table: Tensor, aligned16: bool, E: int, M: int, H: int, W: int, cam_intr, cam_pose: Tensor, vol_origin,
+                               size: float, negate: bool = True, inf_value: float = 100.0, out: Optional[Tensor] = None) -> Tensor:
+    """tasks/hand_base.py:317-324 (stack, negate, inf -> 100) + utils/depth2tsdf.py:146-159 in one pass over the camera images."""
+    assert table.dtype == torch.int64 and table.numel() == E * M and table.is_cuda
+    assert _f32(cam_pose, "cam_pose").is_contiguous() and cam_pose.shape == (M, 4, 4)
+    if out is None:
+        out = torch.empty(E, M * H * W, 3, device=table.device, dtype=torch.float32)
+    intr = (ct.c_float * 9)(*[float(v) for row in cam_intr for v in row])
+    org = (ct.c_float * 3)(*[float(v) for v in vol_origin])
+    check(lib.pm_depth2pc_backproject_views(_p(table), E, M, H, W, int(aligned16), int(negate), float(inf_value), intr, _p(cam_pose), org,
+                                            float(size), _p(out), _stream()), "pm_depth2pc_backproject_views")
+    return out
+
+
 def farthest_point_sample(points: Tensor, K: int, return_idx: bool = False, compact=None):
     """pytorch3d.ops.sample_farthest_points(points, K=K) semantics (start index 0, first index on ties): (E,P,3) -> (E,K,3).
 
-    compact: None/True = auto, False = no compaction, 2 = force the 8-CTA cluster kernel, 3 = force one CTA per cloud."""
+    compact: None/True = auto (P > 48 Ki: one 8-CTA cluster per cloud with exact bounding-box pruning), False = no compaction,
+    2 = streaming cluster kernel, 3 = one CTA per cloud, 4 = pruned cluster kernel."""
     E, P, three = points.shape
     assert three == 3 and _f32(points, "points").is_contiguous()
     out = torch.empty(E, K, 3, device=points.device, dtype=torch.float32)

@@ -1,6 +1,8 @@
 """`TSDFVolume` — the point-cloud half of the reference class (utils/depth2tsdf.py:6-66, 136-173): same constructor,
 `register_camera(cam_pose, cam_intr, im_h, im_w, num_env)` and `depth2pc(depth_im) -> (num_env, 1024, 3)`, with the
 back-projection / workspace mask and the farthest-point sampling (pytorch3d there) running in libpartmanip_b200.so.
+`depth2pc_from_views(camera_tensor_list)` additionally folds in the caller's stacking step (tasks/hand_base.py:317-324 +
+:333): the simulator's per-env, per-view camera tensors are read in place.
 The TSDF-integration half (integrate / sparse_voxel / extract_point_cloud) is outside this row and not mirrored.
 """
 from __future__ import annotations
@@ -33,4 +35,19 @@ class TSDFVolume(object):
         """depth2tsdf.py:136-173: depth_im (b, m, h, w) -> (b, 1024, 3)."""
         assert tuple(depth_im.shape) == tuple(self.registered_shape)
         cloud = ops.depth2pc_backproject(depth_im.float().contiguous(), self.cam_intr, self.cam_pose, self._vol_origin, self._size)
+        return ops.farthest_point_sample(cloud, self.num_points)
+
+    def depth2pc_from_views(self, camera_tensor_list):
+        """tasks/hand_base.py:317-324,333 + depth2tsdf.py:136-173: `camera_tensor_list[env][view]` are the simulator's (h, w) fp32
+        depth images (negative z, -inf background).  Equivalent to
+        `depth2pc(where(isinf(-stack), 100, -stack))` without materialising the stack or the temporaries."""
+        E, M, H, W = self.registered_shape
+        assert len(camera_tensor_list) == E and all(len(v) == M for v in camera_tensor_list)
+        key = tuple(t.data_ptr() for v in camera_tensor_list for t in v)
+        if getattr(self, "_view_key", None) != key:             # Isaac Gym reuses its camera buffers: the table is built once
+            assert all(tuple(t.shape) == (H, W) for v in camera_tensor_list for t in v)
+            self._view_table, self._view_aligned = ops.view_pointer_table(camera_tensor_list)
+            self._view_key = key
+        cloud = ops.depth2pc_backproject_views(self._view_table, self._view_aligned, E, M, H, W, self.cam_intr, self.cam_pose,
+                                               self._vol_origin, self._size, negate=True, inf_value=100.0)
         return ops.farthest_point_sample(cloud, self.num_points)

@@ -138,3 +138,52 @@ def test_fps_pruned_on_depth_image_clouds():
     assert torch.equal(ia, ib) and torch.equal(a, b) and torch.equal(ia, ic)
     want_pts, want_idx = D.farthest_point_sample(cloud[:1].cpu().numpy(), 1024)
     assert np.array_equal(ib[:1].cpu().numpy(), want_idx) and np.array_equal(b[:1].cpu().numpy(), want_pts)
+
+
+@pytest.mark.parametrize("H,W,offset", [(36, 64, 0), (9, 7, 0), (36, 64, 1)])
+def test_backproject_from_camera_tensors_in_place(H, W, offset):
+    """tasks/hand_base.py:317-324 folded into the back-projection: E*M separate simulator images (negative depth, -inf
+    background, some of them not 16-byte aligned) give exactly the cloud of the stacked / negated / inf-replaced tensor."""
+    from partmanip_b200 import ops
+    E, M = 5, 3
+    g = torch.Generator().manual_seed(H * W + offset)
+    views, host = [], []
+    for e in range(E):
+        row, hrow = [], []
+        for m in range(M):
+            raw = -(0.3 + 0.6 * torch.rand(H * W + offset, generator=g))
+            raw[torch.rand(H * W + offset, generator=g) < 0.1] = float("-inf")
+            t = raw.to(DEV)[offset:].view(H, W)                          # offset=1: pointer only 4-byte aligned
+            row.append(t); hrow.append(raw[offset:].view(H, W).numpy())
+        views.append(row); host.append(hrow)
+    intr = np.array([[45.0, 0, W // 2], [0, 45.0, H // 2], [0, 0, 1]])
+    pose = torch.eye(4, device=DEV).repeat(M, 1, 1).contiguous()
+    pose[:, 2, 3] = -0.3
+    table, aligned = ops.view_pointer_table(views)
+    assert aligned == (offset == 0)
+    got = ops.depth2pc_backproject_views(table, aligned, E, M, H, W, intr, pose, [-0.25, -0.25, -0.0503], 0.5)
+    stacked = D.stack_views(host)
+    assert float(stacked.max()) == 100.0
+    same = ops.depth2pc_backproject(torch.from_numpy(stacked).to(DEV), intr, pose, [-0.25, -0.25, -0.0503], 0.5)
+    assert torch.equal(got, same)
+    want = D.backproject(stacked, intr, pose.cpu().numpy(), [-0.25, -0.25, -0.0503], 0.5)
+    g_, w_ = got.cpu().numpy(), want
+    agree = (np.abs(g_).sum(-1) > 0) == (np.abs(w_).sum(-1) > 0)            # a point within 1 ulp of a box face may flip
+    assert agree.mean() > 0.999 and float(np.abs(g_ - w_)[agree].max()) <= 1e-5
+
+
+def test_tsdfvolume_depth2pc_from_views_equals_stacked_path():
+    from partmanip_b200.utils.depth2tsdf import TSDFVolume
+    E, M, H, W = 2, 3, 72, 128
+    g = torch.Generator().manual_seed(3)
+    views = [[(-(0.35 + 0.4 * torch.rand(H, W, generator=g))).to(DEV) for _ in range(M)] for _ in range(E)]
+    views[1][2][:5] = float("-inf")
+    vol = TSDFVolume(DEV, size=0.5, resolution=8)
+    intr = np.array([[90.0, 0, W // 2], [0, 90.0, H // 2], [0, 0, 1]])
+    pose = np.tile(np.eye(4), (M, 1, 1)); pose[:, 2, 3] = -0.3
+    vol.register_camera(pose, intr, H, W, E)
+    a = vol.depth2pc_from_views(views)
+    stacked = -torch.stack([torch.stack(v, 0) for v in views], 0)
+    stacked = torch.where(torch.isinf(stacked), torch.full_like(stacked, 100), stacked)      # hand_base.py:317-324 verbatim semantics
+    b = vol.depth2pc(stacked)
+    assert a.shape == (E, 1024, 3) and torch.equal(a, b)

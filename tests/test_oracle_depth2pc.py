@@ -42,3 +42,17 @@ def test_fps_on_the_reference_cloud_is_deterministic():
     a = D.farthest_point_sample(G["cloud"], 128)[1]
     b = D.farthest_point_sample(G["cloud"].copy(), 128)[1]
     assert (a == b).all() and (a[:, 0] == 0).all()
+
+
+def test_stack_views_matches_torch_semantics():
+    """hand_base.py:317-324: stack per env, stack over envs, negate, isinf -> 100."""
+    import torch
+    rng = np.random.default_rng(0)
+    views = [[-(rng.uniform(0.2, 1.0, (4, 6)).astype(np.float32)) for _ in range(2)] for _ in range(3)]
+    views[1][0][2, 3] = -np.inf
+    views[2][1][0, 0] = np.inf
+    got = D.stack_views(views)
+    t = torch.stack([torch.stack([torch.from_numpy(v) for v in vs], dim=0) for vs in views], dim=0)
+    t = -t
+    t = torch.where(torch.isinf(t), torch.full_like(t, 100), t)
+    assert got.shape == (3, 2, 4, 6) and np.array_equal(got, t.numpy())
