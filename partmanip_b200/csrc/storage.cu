@@ -13,9 +13,20 @@ gather_rows_kernel(const float* __restrict__ src, int64_t lds, const int64_t* __
     const int64_t sr = idx ? idx[r] : r;
     const float* p = src + sr * lds;
     float* q = out + r * ldo;
-    if (VEC == 4) {
-      for (int c = threadIdx.x * 4; c < width; c += blockDim.x * 4)
-        *reinterpret_cast<float4*>(q + c) = __ldg(reinterpret_cast<const float4*>(p + c));
+    if (VEC == 4) {                                        // four 16-byte loads in flight per thread before the first store
+      for (int c0 = threadIdx.x * 4; c0 < width; c0 += blockDim.x * 16) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * blockDim.x * 4;
+          if (c < width) v[u] = __ldg(reinterpret_cast<const float4*>(p + c));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u * blockDim.x * 4;
+          if (c < width) *reinterpret_cast<float4*>(q + c) = v[u];
+        }
+      }
     } else {
       for (int c = threadIdx.x; c < width; c += blockDim.x) q[c] = __ldg(p + c);
     }
