@@ -32,19 +32,32 @@ colreduce_partial(const float* __restrict__ x, int64_t ld, int E, int D, const f
       for (int v = 0; v < VEC; ++v)
         if (col0 + v < D) mu[v] = __fdiv_rn(colsum[col0 + v], count);
     }
-    for (int r = r_begin + threadIdx.y; r < r_end; r += CR_TY) {
-      const float* p = x + (int64_t)r * ld + col0;
-      float val[VEC];
-      if (VEC == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-        val[0] = t.x; val[1 % VEC] = t.y; val[2 % VEC] = t.z; val[3 % VEC] = t.w;
-      } else {
-        val[0] = __ldg(p);
+    // four rows' loads are issued before the first add (HBM latency needs ~40 KB in flight per SM); the adds keep row order
+    constexpr int UR = 4;
+    for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += CR_TY * UR) {
+      float val[UR][VEC];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) {
+        const int r = r0 + u * CR_TY;
+        if (r < r_end) {
+          const float* p = x + (int64_t)r * ld + col0;
+          if (VEC == 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+            val[u][0] = t.x; val[u][1 % VEC] = t.y; val[u][2 % VEC] = t.z; val[u][3 % VEC] = t.w;
+          } else {
+            val[u][0] = __ldg(p);
+          }
+        }
       }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        if (MODE == 0) acc[v] += val[v];
-        else { const float d = val[v] - mu[v]; acc[v] = fmaf(d, d, acc[v]); }
+      for (int u = 0; u < UR; ++u) {
+        if (r0 + u * CR_TY < r_end) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (MODE == 0) acc[v] += val[u][v];
+            else { const float d = val[u][v] - mu[v]; acc[v] = fmaf(d, d, acc[v]); }
+          }
+        }
       }
     }
   }
@@ -99,19 +112,27 @@ rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict
     mu[v] = (col0 + v < D) ? mean[col0 + v] : 0.f;
     sd[v] = (col0 + v < D) ? stdv[col0 + v] : 1.f;
   }
-  for (int r = blockIdx.y; r < E; r += gridDim.y) {
-    const float* p = x + (int64_t)r * ldx + col0;
-    float* q = out + (int64_t)r * ldo + col0;
-    if (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  if (VEC == 4) {                                           // two rows per step: both loads issued before the divisions
+    for (int r = blockIdx.y; r < E; r += 2 * gridDim.y) {
+      const int r2 = r + gridDim.y;
+      float4 t = __ldg(reinterpret_cast<const float4*>(x + (int64_t)r * ldx + col0)), t2 = t;
+      if (r2 < E) t2 = __ldg(reinterpret_cast<const float4*>(x + (int64_t)r2 * ldx + col0));
       t.x = __fdiv_rn(__fsub_rn(t.x, mu[0]), sd[0]);
       t.y = __fdiv_rn(__fsub_rn(t.y, mu[1 % VEC]), sd[1 % VEC]);
       t.z = __fdiv_rn(__fsub_rn(t.z, mu[2 % VEC]), sd[2 % VEC]);
       t.w = __fdiv_rn(__fsub_rn(t.w, mu[3 % VEC]), sd[3 % VEC]);
-      *reinterpret_cast<float4*>(q) = t;
-    } else {
-      q[0] = __fdiv_rn(__fsub_rn(__ldg(p), mu[0]), sd[0]);
+      *reinterpret_cast<float4*>(out + (int64_t)r * ldo + col0) = t;
+      if (r2 < E) {
+        t2.x = __fdiv_rn(__fsub_rn(t2.x, mu[0]), sd[0]);
+        t2.y = __fdiv_rn(__fsub_rn(t2.y, mu[1 % VEC]), sd[1 % VEC]);
+        t2.z = __fdiv_rn(__fsub_rn(t2.z, mu[2 % VEC]), sd[2 % VEC]);
+        t2.w = __fdiv_rn(__fsub_rn(t2.w, mu[3 % VEC]), sd[3 % VEC]);
+        *reinterpret_cast<float4*>(out + (int64_t)r2 * ldo + col0) = t2;
+      }
     }
+  } else {
+    for (int r = blockIdx.y; r < E; r += gridDim.y)
+      out[(int64_t)r * ldo + col0] = __fdiv_rn(__fsub_rn(__ldg(x + (int64_t)r * ldx + col0), mu[0]), sd[0]);
   }
 }
 
