@@ -285,6 +285,18 @@ int pm_fps_cluster_max_active(void);
 int pm_farthest_point_sample(const float* points /* (E,P,3) */, int E, int P, int K, int compact, float* out /* (E,K,3) */,
                              int64_t* out_idx /* (E,K) or NULL */, void* ws, size_t ws_bytes, pm_stream_t s);
 
+/* ------------------------------------------------------------------------------------------
+ * NEXT ROW (first half): depth images -> fused TSDF volume (`depth_tsdf` observations)
+ * pm_tsdf_voxel_tables replaces utils/depth2tsdf.py:14-62 (TSDFVolume.__init__ voxel grid + register_camera's voxel -> pixel
+ * projection): pix_off (M, R^3) = row * W + col of the pixel voxel v = x*R*R + y*R + z projects to in view m, or -1 when it falls
+ * outside the image / behind the camera; pix_z (M, R^3) = its camera-space depth.  cam_intr (3x3), vol_origin (3): HOST arrays.
+ * pm_tsdf_integrate replaces utils/depth2tsdf.py:68-86 (TSDFVolume.integrate): depth (E,M,H,W) -> out (E, R, R, R).
+ * ------------------------------------------------------------------------------------------ */
+int pm_tsdf_voxel_tables(const float* cam_pose_dev /* (M,4,4) */, int M, const float* cam_intr, int H, int W, float size, int resolution,
+                         const float* vol_origin, int32_t* pix_off, float* pix_z, pm_stream_t s);
+int pm_tsdf_integrate(const float* depth, int E, int M, int H, int W, const int32_t* pix_off, const float* pix_z, float size,
+                      int resolution, float default_tsdf, float* out, pm_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -415,6 +415,34 @@ def depth2pc_backproject(depth: Tensor, cam_intr, cam_pose: Tensor, vol_origin, 
     return out
 
 
+def tsdf_voxel_tables(cam_pose: Tensor, cam_intr, im_h: int, im_w: int, size: float, resolution: int, vol_origin) -> Tuple[Tensor, Tensor]:
+    """utils/depth2tsdf.py:14-62: per-view voxel -> pixel tables.  -> pix_off (M, R^3) int32 (row*W+col, -1 invalid), pix_z (M, R^3)."""
+    M = cam_pose.shape[0]
+    assert _f32(cam_pose, "cam_pose").is_contiguous() and cam_pose.shape == (M, 4, 4)
+    R3 = int(resolution) ** 3
+    pix_off = torch.empty(M, R3, device=cam_pose.device, dtype=torch.int32)
+    pix_z = torch.empty(M, R3, device=cam_pose.device, dtype=torch.float32)
+    intr = (ct.c_float * 9)(*[float(v) for row in cam_intr for v in row])
+    org = (ct.c_float * 3)(*[float(v) for v in vol_origin])
+    check(lib.pm_tsdf_voxel_tables(_p(cam_pose), M, intr, int(im_h), int(im_w), float(size), int(resolution), org, _p(pix_off), _p(pix_z),
+                                   _stream()), "pm_tsdf_voxel_tables")
+    return pix_off, pix_z
+
+
+def tsdf_integrate(depth: Tensor, pix_off: Tensor, pix_z: Tensor, size: float, resolution: int, default_tsdf: float = 1.0,
+                   out: Optional[Tensor] = None) -> Tensor:
+    """utils/depth2tsdf.py:68-86: depth (E,M,H,W) fp32 -> fused TSDF volume (E, R, R, R)."""
+    E, M, H, W = depth.shape
+    R = int(resolution)
+    assert _f32(depth, "depth").is_contiguous() and pix_off.dtype == torch.int32 and pix_off.shape == (M, R ** 3) and pix_off.is_contiguous()
+    assert _f32(pix_z, "pix_z").is_contiguous() and pix_z.shape == (M, R ** 3)
+    if out is None:
+        out = torch.empty(E, R, R, R, device=depth.device, dtype=torch.float32)
+    check(lib.pm_tsdf_integrate(_p(depth), E, M, H, W, _p(pix_off), _p(pix_z), float(size), R, float(default_tsdf), _p(out), _stream()),
+          "pm_tsdf_integrate")
+    return out
+
+
 def view_pointer_table(camera_tensor_list) -> Tuple[Tensor, bool]:
     """Device table of the E*M image pointers of `camera_tensor_list[env][view]` (each an (H,W) fp32 CUDA tensor, as Isaac Gym's
     camera tensors are) + whether all of them are 16-byte aligned.  The simulator reuses the buffers, so build it once."""

@@ -3,7 +3,9 @@
 back-projection / workspace mask and the farthest-point sampling (pytorch3d there) running in libpartmanip_b200.so.
 `depth2pc_from_views(camera_tensor_list)` additionally folds in the caller's stacking step (tasks/hand_base.py:317-324 +
 :333): the simulator's per-env, per-view camera tensors are read in place.
-The TSDF-integration half (integrate / sparse_voxel / extract_point_cloud) is outside this row and not mirrored.
+`integrate(depth_im) -> (num_env, R, R, R)` (depth2tsdf.py:68-86) runs on the voxel -> pixel tables `register_camera` builds with
+`pm_tsdf_voxel_tables` (the reference's `valid_pix*` / `pix_z` tensors, packed).  `sparse_voxel` (needs a ragged farthest-point
+sampler over voxel indices) and `extract_point_cloud` (CPU marching cubes via skimage, debugging only) are not mirrored.
 """
 from __future__ import annotations
 
@@ -30,6 +32,16 @@ class TSDFVolume(object):
         self.registered_shape = (num_env, cam_pose.shape[0], im_h, im_w)
         self.cam_pose = torch.tensor(cam_pose, device=self.device).float().contiguous()     # (m, 4, 4); identical for every env
         self.cam_intr = np.asarray(cam_intr, dtype=np.float64)
+        self.pix_off, self.pix_z = ops.tsdf_voxel_tables(self.cam_pose, self.cam_intr, im_h, im_w, self._size, self._resolution,
+                                                         self._vol_origin)
+        self.default_tsdf = 1
+
+    def integrate(self, depth_im):
+        """depth2tsdf.py:68-86: depth_im (b, m, h, w) -> fused TSDF volume (b, R, R, R); also kept as `_tsdf_vol` like the reference."""
+        assert tuple(depth_im.shape) == tuple(self.registered_shape)
+        self._tsdf_vol = ops.tsdf_integrate(depth_im.float().contiguous(), self.pix_off, self.pix_z, self._size, self._resolution,
+                                            float(self.default_tsdf))
+        return self._tsdf_vol
 
     def depth2pc(self, depth_im):
         """depth2tsdf.py:136-173: depth_im (b, m, h, w) -> (b, 1024, 3)."""
