@@ -4,7 +4,10 @@ Restates /root/reference/utils/depth2tsdf.py with numpy, float32 throughout:
   * `voxel_pixel_tables` = the per-view voxel -> pixel tables of `TSDFVolume.__init__` + `register_camera` (:14-62);
   * `integrate` = `TSDFVolume.integrate` (:68-86): gather one depth pixel per (view, voxel), truncated signed distance,
     equal-weight average over the views that see the voxel in front of / inside the band, 1 where none does.
-PINNED: tests/golden/tsdf_small.npz holds the tables and the volume the UNMODIFIED reference computes for a seeded input
+  * `sparse_voxel` = the rest of `TSDFVolume.sparse_voxel` (:103-119): band select in torch.where order, pytorch3d farthest-point
+    sampling on the integer voxel coordinates (restated in oracle/depth2pc_oracle.py — pytorch3d is absent: that step is
+    PARITY UNPINNED), gather of the TSDF values.
+PINNED (tables and fusion): tests/golden/tsdf_small.npz holds the tables and the volume the UNMODIFIED reference computes for a seeded input
 (tests/golden/make_golden_tsdf.py).  Only tests/ may import this module."""
 from __future__ import annotations
 
@@ -57,3 +60,21 @@ def integrate(depth, pix_x, pix_y, pix_z, valid, size: float, resolution: int, d
         acc = (acc + prod[:, m]).astype(np.float32)
     vol = (acc + np.float32(default_tsdf) * (cnt == 0)).astype(np.float32)
     return vol.reshape(E, R, R, R)
+
+
+def sparse_voxel(tsdf_vol, K: int = 1024, lo: float = -0.2, hi: float = 0.2):
+    """tsdf_vol (E, R, R, R) fp32 -> (E, K, 4) fp32 = (x, y, z, tsdf) of K farthest-point-sampled band voxels (:103-119)."""
+    from .depth2pc_oracle import farthest_point_sample
+    vol = np.asarray(tsdf_vol, np.float32)
+    out = np.zeros((vol.shape[0], K, 4), np.float32)
+    for e in range(vol.shape[0]):
+        ind = np.argwhere((vol[e] < np.float32(hi)) & (vol[e] > np.float32(lo)))                 # row-major, as torch.where
+        if len(ind) == 0:                                              # the reference fails on an empty band; the kernel returns voxel 0
+            ind = np.zeros((1, 3), np.int64)
+        _, idx = farthest_point_sample(ind[None].astype(np.float32), K)
+        sel = ind[idx[0]]
+        if len(sel) < K:                                               # fewer band voxels than K: the samplers repeat the first one
+            sel = np.concatenate([sel, np.repeat(sel[:1], K - len(sel), axis=0)])
+        out[e, :, :3] = sel
+        out[e, :, 3] = vol[e][sel[:, 0], sel[:, 1], sel[:, 2]]
+    return out

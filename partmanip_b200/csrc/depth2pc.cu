@@ -750,6 +750,58 @@ fps_cluster_pruned_kernel(const float* __restrict__ cp, const int32_t* __restric
 #undef FPS_PR_LOAD
 #undef FPS_PR_GG
 
+// ---- sparse voxels (utils/depth2tsdf.py:88-120, TSDFVolume.sparse_voxel): the voxels whose fused TSDF lies strictly inside
+//      (lo, hi), in row-major (x, y, z) order (torch.where), farthest-point-sampled on their integer coordinates, returned as
+//      (x, y, z, tsdf).  The band test is an ordered compaction that writes straight into the samplers' compacted-cloud layout
+//      (coordinates as exact fp32 integers, voxel number as the original index), so the picks come from fps_compacted_kernel.
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+tsdf_band_compact_kernel(const float* __restrict__ tsdf /* (E, R3) */, int R, int R3, int Pp /* R3 rounded up to 4 */, float lo, float hi,
+                         float* __restrict__ cp /* (E, Pp+4, 3) */, int32_t* __restrict__ om /* (E, Pp+4) */, int32_t* __restrict__ counts) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* t = tsdf + (int64_t)e * R3;
+  float* c = cp + (int64_t)e * (Pp + 4) * 3;
+  int32_t* o = om + (int64_t)e * (Pp + 4);
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < R3; base += FPS_THREADS) {
+    const int v = base + tid;
+    bool keep = false;
+    if (v < R3) { const float x = t[v]; keep = x < hi && x > lo; }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int w = 0; w < 32; ++w) { const int n = s_warp[w]; if (w < warp) woff += n; total += n; }
+    const int carry = s_carry;
+    if (keep) {
+      const int pos = carry + woff + __popc(mask & ((1u << lane) - 1u));
+      c[(int64_t)pos * 3] = (float)(v / (R * R)); c[(int64_t)pos * 3 + 1] = (float)((v / R) % R); c[(int64_t)pos * 3 + 2] = (float)(v % R);
+      o[pos] = v;
+    }
+    __syncthreads();
+    if (tid == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int n = s_carry;
+    if (n == 0) { c[0] = 0.f; c[1] = 0.f; c[2] = 0.f; o[0] = 0; n = 1; }    // empty band (the reference would fail): voxel 0 stands in
+    counts[e] = n;
+    while (n & 3) { c[(int64_t)n * 3] = c[0]; c[(int64_t)n * 3 + 1] = c[1]; c[(int64_t)n * 3 + 2] = c[2]; o[n] = o[0]; ++n; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+tsdf_sparse_gather_kernel(const float* __restrict__ tsdf, int R3, const float* __restrict__ pts /* (E,K,3) */, const int64_t* __restrict__ idx,
+                          int E, int K, float* __restrict__ out /* (E,K,4) */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= E * K) return;
+  const int e = i / K;
+  reinterpret_cast<float4*>(out)[i] = make_float4(pts[(int64_t)i * 3], pts[(int64_t)i * 3 + 1], pts[(int64_t)i * 3 + 2],
+                                                  tsdf[(int64_t)e * R3 + idx[i]]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -869,6 +921,35 @@ int pm_farthest_point_sample(const float* points, int E, int P, int K, int compa
     else fps_kernel<false, false><<<E, FPS_THREADS, 0, pm_st(s)>>>(points, P, K, reinterpret_cast<float*>(ws), out, out_idx);
   }
   PM_CHECK_LAUNCH("pm_farthest_point_sample");
+  return PM_OK;
+}
+
+// workspace: [pm_fps_ws_bytes(E, R^3 rounded up to 4) | picked points (E,K,3) | picked voxel numbers (E,K) int64]
+size_t pm_tsdf_sparse_voxel_ws_bytes(int E, int resolution, int K) {
+  const int Pp = (resolution * resolution * resolution + 3) & ~3;
+  return pm_align_up(pm_fps_ws_bytes(E, Pp), 256) + pm_align_up((size_t)E * K * 12, 256) + pm_align_up((size_t)E * K * 8, 256);
+}
+
+int pm_tsdf_sparse_voxel(const float* tsdf, int E, int resolution, float lo, float hi, int K, float* out, void* ws, size_t ws_bytes,
+                         pm_stream_t s) {
+  PM_REQUIRE(tsdf && out && ws, PM_ERR_ARG, "pm_tsdf_sparse_voxel: null pointer");
+  PM_REQUIRE(E > 0 && resolution > 0 && resolution <= 512 && K > 0, PM_ERR_SHAPE, "pm_tsdf_sparse_voxel: E=%d resolution=%d K=%d", E, resolution, K);
+  PM_REQUIRE(ws_bytes >= pm_tsdf_sparse_voxel_ws_bytes(E, resolution, K) && pm_aligned(ws, 256) && pm_aligned(out, 16), PM_ERR_ARG,
+             "pm_tsdf_sparse_voxel: workspace too small / unaligned");
+  const int R3 = resolution * resolution * resolution, Pp = (R3 + 3) & ~3;
+  char* base = reinterpret_cast<char*>(ws);
+  float* cp = reinterpret_cast<float*>(base);
+  int32_t* om = reinterpret_cast<int32_t*>(base + pm_align_up((size_t)E * (Pp + 4) * 12, 256));
+  int32_t* counts = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(om) + pm_align_up((size_t)E * (Pp + 4) * 4, 256));
+  float* mind = reinterpret_cast<float*>(reinterpret_cast<char*>(counts) + pm_align_up((size_t)E * 4, 256));
+  float* pts = reinterpret_cast<float*>(base + pm_align_up(pm_fps_ws_bytes(E, Pp), 256));
+  int64_t* idx = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(pts) + pm_align_up((size_t)E * K * 12, 256));
+  cudaError_t e1 = cudaFuncSetAttribute(fps_compacted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FPS_SMEM_POINTS * 4);
+  if (e1 != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e1));
+  tsdf_band_compact_kernel<<<E, FPS_THREADS, 0, pm_st(s)>>>(tsdf, resolution, R3, Pp, lo, hi, cp, om, counts);
+  fps_compacted_kernel<<<E, FPS_THREADS, FPS_SMEM_POINTS * 4, pm_st(s)>>>(cp, om, counts, Pp, K, mind, pts, idx);
+  tsdf_sparse_gather_kernel<<<(E * K + 255) / 256, 256, 0, pm_st(s)>>>(tsdf, R3, pts, idx, E, K, out);
+  PM_CHECK_LAUNCH("pm_tsdf_sparse_voxel");
   return PM_OK;
 }
 

@@ -443,6 +443,18 @@ def tsdf_integrate(depth: Tensor, pix_off: Tensor, pix_z: Tensor, size: float, r
     return out
 
 
+def tsdf_sparse_voxel(tsdf_vol: Tensor, K: int = 1024, lo: float = -0.2, hi: float = 0.2) -> Tensor:
+    """utils/depth2tsdf.py:103-119: voxels with lo < tsdf < hi -> K farthest (on integer coordinates) -> (E, K, 4) = (x, y, z, tsdf)."""
+    E, R = tsdf_vol.shape[0], tsdf_vol.shape[1]
+    assert _f32(tsdf_vol, "tsdf_vol").is_contiguous() and tuple(tsdf_vol.shape) == (E, R, R, R)
+    out = torch.empty(E, K, 4, device=tsdf_vol.device, dtype=torch.float32)
+    nbytes = lib.pm_tsdf_sparse_voxel_ws_bytes(E, R, int(K))
+    ws = scratch(nbytes, tsdf_vol.device, "fps")
+    check(lib.pm_tsdf_sparse_voxel(_p(tsdf_vol), E, R, float(lo), float(hi), int(K), _p(out), _p(ws), nbytes, _stream()),
+          "pm_tsdf_sparse_voxel")
+    return out
+
+
 def view_pointer_table(camera_tensor_list) -> Tuple[Tensor, bool]:
     """Device table of the E*M image pointers of `camera_tensor_list[env][view]` (each an (H,W) fp32 CUDA tensor, as Isaac Gym's
     camera tensors are) + whether all of them are 16-byte aligned.  The simulator reuses the buffers, so build it once."""

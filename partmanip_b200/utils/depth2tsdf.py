@@ -4,8 +4,9 @@ back-projection / workspace mask and the farthest-point sampling (pytorch3d ther
 `depth2pc_from_views(camera_tensor_list)` additionally folds in the caller's stacking step (tasks/hand_base.py:317-324 +
 :333): the simulator's per-env, per-view camera tensors are read in place.
 `integrate(depth_im) -> (num_env, R, R, R)` (depth2tsdf.py:68-86) runs on the voxel -> pixel tables `register_camera` builds with
-`pm_tsdf_voxel_tables` (the reference's `valid_pix*` / `pix_z` tensors, packed).  `sparse_voxel` (needs a ragged farthest-point
-sampler over voxel indices) and `extract_point_cloud` (CPU marching cubes via skimage, debugging only) are not mirrored.
+`pm_tsdf_voxel_tables` (the reference's `valid_pix*` / `pix_z` tensors, packed); `sparse_voxel(depth_im) -> (num_env, 1024, 4)`
+(depth2tsdf.py:88-120, the `depth_sparse` observation) fuses, selects the |tsdf| < 0.2 band and farthest-point-samples it.
+`extract_point_cloud` (CPU marching cubes via skimage, debugging only) is not mirrored.
 """
 from __future__ import annotations
 
@@ -42,6 +43,14 @@ class TSDFVolume(object):
         self._tsdf_vol = ops.tsdf_integrate(depth_im.float().contiguous(), self.pix_off, self.pix_z, self._size, self._resolution,
                                             float(self.default_tsdf))
         return self._tsdf_vol
+
+    def sparse_voxel(self, depth_im):
+        """depth2tsdf.py:88-120: (b, m, h, w) -> (b, 1024, 4) = 1024 farthest band voxels (x, y, z, tsdf).  Unlike `integrate`, the
+        reference does not keep the volume in `_tsdf_vol` here."""
+        assert tuple(depth_im.shape) == tuple(self.registered_shape)
+        vol = ops.tsdf_integrate(depth_im.float().contiguous(), self.pix_off, self.pix_z, self._size, self._resolution,
+                                 float(self.default_tsdf))
+        return ops.tsdf_sparse_voxel(vol, self.num_points, -0.2, 0.2)
 
     def depth2pc(self, depth_im):
         """depth2tsdf.py:136-173: depth_im (b, m, h, w) -> (b, 1024, 3)."""

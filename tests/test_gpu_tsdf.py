@@ -75,3 +75,49 @@ def test_integrate_empty_scene_keeps_default():
     for fill in (0.0, 100.0, 1e-3):
         out = ops.tsdf_integrate(torch.full((2, M, H, W), fill, device=DEV), pix_off, pix_z, float(G["size"]), R)
         assert bool((out == 1).all())
+
+
+def _smooth_volume(E, R, seed):
+    """A synthetic fused volume: signed distance to a wavy sheet, clamped like the reference's (values in (-1, 1], 1 = free)."""
+    rng = np.random.default_rng(seed)
+    x, y, z = np.meshgrid(np.arange(R), np.arange(R), np.arange(R), indexing="ij")
+    vols = []
+    for e in range(E):
+        a, b, c = rng.uniform(0.1, 0.4, 3)
+        h = R * (0.5 + 0.2 * np.sin(a * x + e) * np.cos(b * y)) + c
+        vols.append(np.clip((h - z) / 4.0, -1, 1))
+    v = np.stack(vols).astype(np.float32)
+    v[v <= -0.99] = 1.0
+    return v
+
+
+@pytest.mark.parametrize("E,R,K", [(3, 12, 48), (2, 50, 1024), (2, 5, 16), (1, 31, 200)])
+def test_sparse_voxel_matches_oracle(E, R, K):
+    from partmanip_b200 import ops
+    vol = G["tsdf"] if R == 12 else _smooth_volume(E, R, R)
+    want = T.sparse_voxel(vol, K)
+    got = ops.tsdf_sparse_voxel(torch.from_numpy(vol).to(DEV), K).cpu().numpy()
+    assert np.array_equal(got, want)                                   # integer coordinates: index-exact picks, gathered values
+
+
+def test_sparse_voxel_empty_and_small_bands():
+    from partmanip_b200 import ops
+    v = np.ones((2, 6, 6, 6), np.float32)
+    v[1, 1, 2, 3] = 0.05
+    v[1, 5, 0, 1] = -0.1
+    v[1, 2, 2, 2] = 0.2                                                  # on the threshold: excluded (strict comparisons)
+    got = ops.tsdf_sparse_voxel(torch.from_numpy(v).to(DEV), 7).cpu().numpy()
+    assert np.array_equal(got, T.sparse_voxel(v, 7))
+    assert (got[0] == np.array([0, 0, 0, 1], np.float32)).all()
+    assert got[1, :2].tolist() == [[1, 2, 3, np.float32(0.05)], [5, 0, 1, np.float32(-0.1)]]
+
+
+def test_tsdfvolume_sparse_voxel_end_to_end():
+    from partmanip_b200.utils.depth2tsdf import TSDFVolume
+    E, M, H, W = G["depth"].shape
+    vol = TSDFVolume(DEV, size=float(G["size"]), resolution=int(G["resolution"]), _vol_origin=G["vol_origin"].tolist())
+    vol.register_camera(G["cam_pose"], G["cam_intr"], H, W, E)
+    vol.num_points = 40
+    out = vol.sparse_voxel(torch.from_numpy(G["depth"]).to(DEV)).cpu().numpy()
+    fused = vol.integrate(torch.from_numpy(G["depth"]).to(DEV)).cpu().numpy()
+    assert np.array_equal(out, T.sparse_voxel(fused, 40))

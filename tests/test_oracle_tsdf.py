@@ -42,3 +42,27 @@ def test_integrate_edge_cases():
     # a surface in front of every voxel (occluded beyond the band): no view is valid -> default 1
     vol = T.integrate(np.full((1, M, H, W), 1e-3, np.float32), px, py, pz, valid, float(G["size"]), R)
     assert (vol == 1).all()
+
+
+def test_sparse_voxel_properties():
+    """depth2tsdf.py:103-119: the picks are band voxels, start at the first one in row-major order, are distinct while the band
+    lasts, and carry their own TSDF value."""
+    vol = G["tsdf"]
+    band = (vol < 0.2) & (vol > -0.2)
+    K = 48
+    out = T.sparse_voxel(vol, K)
+    assert out.shape == (vol.shape[0], K, 4) and out.dtype == np.float32
+    for e in range(vol.shape[0]):
+        xyz = out[e, :, :3].astype(np.int64)
+        assert band[e][xyz[:, 0], xyz[:, 1], xyz[:, 2]].all()
+        assert (xyz[0] == np.argwhere(band[e])[0]).all()
+        n = min(K, int(band[e].sum()))
+        assert len({tuple(v) for v in xyz[:n]}) == n
+        assert np.array_equal(out[e, :, 3], vol[e][xyz[:, 0], xyz[:, 1], xyz[:, 2]])
+    # empty band / band smaller than K: defined behaviour of the kernel (voxel 0 / repeats of the first band voxel)
+    v2 = np.ones((1, 4, 4, 4), np.float32)
+    assert (T.sparse_voxel(v2, 8) == np.array([0, 0, 0, 1], np.float32)).all()
+    v2[0, 1, 2, 3] = 0.05
+    v2[0, 3, 0, 1] = -0.1
+    o = T.sparse_voxel(v2, 5)[0]
+    assert o[:2].tolist() == [[1, 2, 3, np.float32(0.05)], [3, 0, 1, np.float32(-0.1)]] and (o[2:] == o[0]).all()
