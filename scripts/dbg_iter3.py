@@ -1,3 +1,6 @@
+"""Dev tool: shows that the 40-step Adam trajectory of the full-iteration test is chaotic in the max-pool arg-max — two of our own
+kernel variants whose single-step gradients agree to 1e-7 drift apart as much as either does from the reference recording
+(the reason the full-iteration weight gate in tests/test_gpu_pointnet_ppo.py is statistical)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
