@@ -16,6 +16,12 @@ import torch
 from .. import ops
 
 
+def env_chunks(num_env: int, chunk: int):
+    """[lo, hi) env ranges of at most `chunk` envs covering 0..num_env in order."""
+    chunk = max(1, int(chunk))
+    return [(lo, min(lo + chunk, num_env)) for lo in range(0, num_env, chunk)]
+
+
 class TSDFVolume(object):
     def __init__(self, device, size=0.5, resolution=50, _vol_origin=(-0.25, -0.25, -0.0503)):
         if not str(device).startswith("cuda"):
@@ -26,6 +32,10 @@ class TSDFVolume(object):
         self.device = device
         self._vol_origin = [float(v) for v in _vol_origin]
         self.num_points = 1024                                  # depth2tsdf.py:160 hard-codes K=1024
+        # depth2pc materialises the full-resolution cloud (m*h*w points per env: 5.3 MB at 3 x 288 x 512) and the samplers'
+        # workspace (20 B per point) before reducing it to 1024 points; envs are processed this many at a time so that 4096
+        # envs need 3.7 GB of transient memory instead of 58 GB.  The result does not depend on it (clouds are independent).
+        self.env_chunk = 256
 
     def register_camera(self, cam_pose, cam_intr, im_h, im_w, num_env):
         """depth2tsdf.py:31-66 (the camera bookkeeping depth2pc needs)."""
@@ -55,8 +65,18 @@ class TSDFVolume(object):
     def depth2pc(self, depth_im):
         """depth2tsdf.py:136-173: depth_im (b, m, h, w) -> (b, 1024, 3)."""
         assert tuple(depth_im.shape) == tuple(self.registered_shape)
-        cloud = ops.depth2pc_backproject(depth_im.float().contiguous(), self.cam_intr, self.cam_pose, self._vol_origin, self._size)
-        return ops.farthest_point_sample(cloud, self.num_points)
+        depth_im = depth_im.float().contiguous()
+        E = depth_im.shape[0]
+        out = None
+        for lo, hi in env_chunks(E, self.env_chunk):
+            cloud = ops.depth2pc_backproject(depth_im[lo:hi], self.cam_intr, self.cam_pose, self._vol_origin, self._size)
+            pc = ops.farthest_point_sample(cloud, self.num_points)
+            if lo == 0 and hi == E:
+                return pc
+            if out is None:
+                out = torch.empty(E, self.num_points, 3, device=pc.device, dtype=pc.dtype)
+            out[lo:hi] = pc
+        return out
 
     def depth2pc_from_views(self, camera_tensor_list):
         """tasks/hand_base.py:317-324,333 + depth2tsdf.py:136-173: `camera_tensor_list[env][view]` are the simulator's (h, w) fp32
@@ -69,6 +89,14 @@ class TSDFVolume(object):
             assert all(tuple(t.shape) == (H, W) for v in camera_tensor_list for t in v)
             self._view_table, self._view_aligned = ops.view_pointer_table(camera_tensor_list)
             self._view_key = key
-        cloud = ops.depth2pc_backproject_views(self._view_table, self._view_aligned, E, M, H, W, self.cam_intr, self.cam_pose,
-                                               self._vol_origin, self._size, negate=True, inf_value=100.0)
-        return ops.farthest_point_sample(cloud, self.num_points)
+        out = None
+        for lo, hi in env_chunks(E, self.env_chunk):
+            cloud = ops.depth2pc_backproject_views(self._view_table[lo * M:hi * M], self._view_aligned, hi - lo, M, H, W, self.cam_intr,
+                                                   self.cam_pose, self._vol_origin, self._size, negate=True, inf_value=100.0)
+            pc = ops.farthest_point_sample(cloud, self.num_points)
+            if lo == 0 and hi == E:
+                return pc
+            if out is None:
+                out = torch.empty(E, self.num_points, 3, device=pc.device, dtype=pc.dtype)
+            out[lo:hi] = pc
+        return out
