@@ -20,62 +20,40 @@ from .. import ops
 from .algo_utils import ActorCritic, RolloutStorage
 from .ppo import FlatAdam
 
+# attribute <- cfg key (dagger.py:18-51); the attribute names are the reference's, other code reads them
+_CFG_ATTRS = (("num_envs", "num_envs"), ("stu_obs_mode", "obs_mode"), ("model_cfg", "model"), ("max_iter", "max_iterations"),
+              ("n_steps", "n_steps"), ("n_updates", "n_updates"), ("num_mini_batches", "n_minibatches"), ("device", "device"),
+              ("buf_size", "buf_size"), ("reward_reset", "reward_reset"), ("add_proprio_obs", "add_proprio_obs"),
+              ("offline_data_pth", "offline_data_pth"), ("eval_round", "eval_round"), ("eval_freq", "eval_frequence"),
+              ("save_freq", "save_frequence"), ("test_only", "test_only"), ("save_pose", "save_pose"), ("save_video", "save_video"),
+              ("lr_schedule", "lr_schedule"), ("lr", "lr"), ("teacher_path", "teacher"))
+_REWARD_RESET_LAG = 10                                              # dagger.py:229 `delta_step`
+
+
+def _action_summaries(infos, actions):
+    """The three action statistics both loops log (dagger.py:159-161, 222-224)."""
+    infos['action_t'] = actions[:, :3].mean(dim=-1)
+    infos['action_r'] = actions[:, 3:6].mean(dim=-1)
+    infos['action_gripper'] = actions[:, -1]
+    return infos
+
 
 class dagger:
     def __init__(self, vec_env, cfg, logger):
-        self.vec_env = vec_env
-        self.num_envs = cfg['num_envs']
-        self.stu_obs_mode = cfg['obs_mode']
-        self.stu_num_obs = vec_env.num_obs[self.stu_obs_mode]
-        self.stu_input_obs = self.stu_num_obs
-        self.num_actions = vec_env.num_actions
-        self.max_episode_length = vec_env.max_episode_length
-        self.model_cfg = cfg['model']
-        self.max_iter = cfg['max_iterations']
-        self.n_steps = cfg['n_steps']
-        self.n_updates = cfg['n_updates']
-        self.num_mini_batches = cfg['n_minibatches']
-        self.device = cfg['device']
-        self.buf_size = cfg['buf_size']
-        self.reward_reset = cfg['reward_reset']
-        if self.reward_reset:
-            self.tea_rew = torch.tensor(np.load('teacher_reward.npy')).to(self.device)
-        self.add_proprio_obs = cfg['add_proprio_obs']
-        self.offline_data_pth = cfg['offline_data_pth']
+        self.vec_env, self.logger = vec_env, logger
+        for attr, key in _CFG_ATTRS:
+            setattr(self, attr, cfg[key])
         if self.offline_data_pth is not None:
             raise NotImplementedError("offline TSDF replay (storage.add_transitions_offline) is outside the hot path")
-        self.eval_round = cfg['eval_round']
-        self.eval_freq = cfg['eval_frequence']
-        self.save_freq = cfg['save_frequence']
-        self.test_only = cfg['test_only']
-        self.save_pose = cfg['save_pose']
-        self.save_video = cfg['save_video']
+        if self.reward_reset:
+            self.tea_rew = torch.tensor(np.load('teacher_reward.npy')).to(self.device)
+        self.stu_num_obs = self.stu_input_obs = vec_env.num_obs[self.stu_obs_mode]
+        self.num_actions = vec_env.num_actions
+        self.max_episode_length = vec_env.max_episode_length
         self.save_ckpt_dir = logger.save_ckpt_dir
-        self.lr_schedule = cfg['lr_schedule']
-        self.lr = cfg['lr']
-        # student (dagger.py:53-56): one Adam over all student parameters; only the actor ever receives a gradient,
-        # and torch's Adam skips grad-less tensors, so the flat optimiser covers exactly the actor block
-        self.student = ActorCritic(self.stu_input_obs, self.num_actions, self.model_cfg,
-                                   cfg['add_proprio_obs'] * vec_env.num_obs['proprio_state']).to(self.device)
-        st = self.student.flatten_()
-        a_params = list(st.actor.parameters())
-        n_actor = st.actor_n_clip
-        self.optimizer = FlatAdam(st.actor_flat[:n_actor], a_params, st.actor_offs[:-1], [len(a_params)], self.lr, 0, 0.0)
-        self._grads = [self.optimizer.grad[o:o + p.numel()].view(p.shape) for p, o in zip(a_params, st.actor_offs[:-1])]
-        self.logger = logger
-        self.total_envsteps = 0
-        self.total_time = 0
-        self.curr_iter = 0
-        # teacher (dagger.py:64-73)
-        self.teacher_path = cfg['teacher']
-        assert self.teacher_path is not None and os.path.exists(self.teacher_path)
-        print(f'load teacher ckpt from {self.teacher_path}!')
-        tea_dict = torch.load(self.teacher_path, map_location=self.device, weights_only=False)
-        self.tea_obs_mode = tea_dict['obs_mode']
-        self.tea_num_obs = vec_env.num_obs[self.tea_obs_mode]
-        self.teacher = ActorCritic(self.tea_num_obs, self.num_actions, tea_dict['model_cfg']).to(self.device)
-        self.teacher.load_state_dict(tea_dict["model_state_dict"])
-        assert tea_dict['tricks']['use_state_norm'] == False  # noqa: E712  (dagger.py:73)
+        self.total_envsteps = self.total_time = self.curr_iter = 0
+        self._build_student(vec_env.num_obs['proprio_state'] * self.add_proprio_obs)
+        self._load_teacher()
         self.resume(cfg['resume'])
         self.load_pretrain(cfg['pretrain'])
         self.storage = RolloutStorage(self.num_envs, self.buf_size, self.stu_num_obs, self.num_actions, self.device,
@@ -85,121 +63,142 @@ class dagger:
         self._acc = torch.zeros(2, device=self.device)
         self._mb = {}
 
+    def _build_student(self, proprio_dim):
+        """dagger.py:53-56: one Adam over all student parameters.  Only the actor ever receives a gradient and torch's Adam skips
+        grad-less tensors, so the flat optimiser covers exactly the actor block."""
+        self.student = ActorCritic(self.stu_input_obs, self.num_actions, self.model_cfg, proprio_dim).to(self.device)
+        flat = self.student.flatten_()
+        tensors = list(flat.actor.parameters())
+        offsets = flat.actor_offs[:-1]
+        self.optimizer = FlatAdam(flat.actor_flat[:flat.actor_n_clip], tensors, offsets, [len(tensors)], self.lr, 0, 0.0)
+        self._grads = [self.optimizer.grad[o:o + t.numel()].view(t.shape) for t, o in zip(tensors, offsets)]
+
+    def _load_teacher(self):
+        """dagger.py:64-73: a frozen state-based ActorCritic trained without observation normalisation."""
+        assert self.teacher_path is not None and os.path.exists(self.teacher_path)
+        print(f'load teacher ckpt from {self.teacher_path}!')
+        ckpt = torch.load(self.teacher_path, map_location=self.device, weights_only=False)
+        assert ckpt['tricks']['use_state_norm'] == False  # noqa: E712  (dagger.py:73)
+        self.tea_obs_mode = ckpt['obs_mode']
+        self.tea_num_obs = self.vec_env.num_obs[self.tea_obs_mode]
+        self.teacher = ActorCritic(self.tea_num_obs, self.num_actions, ckpt['model_cfg']).to(self.device)
+        self.teacher.load_state_dict(ckpt["model_state_dict"])
+
+    # ------------------------------------------------------------------ checkpoints (dagger.py:85-112)
     def save(self, it):
         os.makedirs(self.save_ckpt_dir, exist_ok=True)
-        save_path = pjoin(self.save_ckpt_dir, f'model_{it}.pth')
-        torch.save({'iteration': it,
-                    'model_state_dict': {k: v.detach().clone() for k, v in self.student.state_dict().items()},
-                    'optimizer_state_dict': self.optimizer.state_dict(), 'total_steps': self.total_envsteps,
-                    'obs_mode': self.stu_obs_mode, 'teacher': self.teacher_path}, save_path)
-        print(f'save ckpt to {save_path}!')
+        target = pjoin(self.save_ckpt_dir, f'model_{it}.pth')
+        weights = {name: t.detach().clone() for name, t in self.student.state_dict().items()}
+        torch.save(dict(iteration=it, model_state_dict=weights, optimizer_state_dict=self.optimizer.state_dict(),
+                        total_steps=self.total_envsteps, obs_mode=self.stu_obs_mode, teacher=self.teacher_path), target)
+        print(f'save ckpt to {target}!')
+
+    def _read_ckpt(self, ckpt_path):
+        assert os.path.exists(ckpt_path)
+        return torch.load(ckpt_path, map_location=self.device, weights_only=False)
 
     def load_pretrain(self, ckpt_path):
-        if ckpt_path is not None:
-            assert os.path.exists(ckpt_path)
-            ckpt_dict = torch.load(ckpt_path, map_location=self.device, weights_only=False)
-            ckpt_dict['model_state_dict'].pop('log_std')
-            self.student.load_state_dict(ckpt_dict["model_state_dict"], strict=False)
+        if ckpt_path is None:
+            return
+        weights = self._read_ckpt(ckpt_path)['model_state_dict']
+        weights.pop('log_std')
+        self.student.load_state_dict(weights, strict=False)
 
     def resume(self, ckpt_path):
-        if ckpt_path is not None:
-            assert os.path.exists(ckpt_path)
-            ckpt_dict = torch.load(ckpt_path, map_location=self.device, weights_only=False)
-            self.student.load_state_dict(ckpt_dict["model_state_dict"])
-            self.optimizer.load_state_dict(ckpt_dict["optimizer_state_dict"])
-            self.curr_iter = ckpt_dict["iteration"]
-            self.total_envsteps = ckpt_dict["total_steps"]
+        if ckpt_path is None:
+            return
+        ckpt = self._read_ckpt(ckpt_path)
+        self.student.load_state_dict(ckpt["model_state_dict"])
+        self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        self.curr_iter, self.total_envsteps = ckpt["iteration"], ckpt["total_steps"]
 
+    # ------------------------------------------------------------------ evaluation (dagger.py:114-178)
     def eval(self):
         self.student.eval()
         if self.test_only:
             self.log_dict = {}
-        for r in range(self.eval_round):
-            ep_infos = []
-            all_curr_obs = self.vec_env.reset()
-            stu_curr_obs = all_curr_obs[self.stu_obs_mode]
-            for i in range(self.max_episode_length):
-                actions = self.student.act(stu_curr_obs)
-                save_image_path = (pjoin(self.logger.save_video_dir, f"Iter{self.curr_iter}", f"{i}.png")
-                                   if self.save_video else None)
-                next_obs, rews, dones, infos = self.vec_env.step(actions, save_image_path=save_image_path)
-                infos['action_t'] = actions[:, :3].mean(dim=-1)
-                infos['action_r'] = actions[:, 3:6].mean(dim=-1)
-                infos['action_gripper'] = actions[:, -1]
-                infos['reward'] = rews
-                ep_infos.append(deepcopy(infos))
-                stu_curr_obs = next_obs[self.stu_obs_mode]
-            self.use_info_update_logdict(ep_infos, 'Test' if self.test_only else 'Val')
+        mode = 'Test' if self.test_only else 'Val'
+        for _ in range(self.eval_round):
+            episode = []
+            obs = self.vec_env.reset()[self.stu_obs_mode]
+            for t in range(self.max_episode_length):
+                actions = self.student.act(obs)
+                frame = pjoin(self.logger.save_video_dir, f"Iter{self.curr_iter}", f"{t}.png") if self.save_video else None
+                nxt, rews, _, infos = self.vec_env.step(actions, save_image_path=frame)
+                _action_summaries(infos, actions)['reward'] = rews
+                episode.append(deepcopy(infos))
+                obs = nxt[self.stu_obs_mode]
+            self.use_info_update_logdict(episode, mode)
+
+    # ------------------------------------------------------------------ training loop (dagger.py:180-278)
+    def _reset_env(self):
+        first = self.vec_env.reset()
+        return first[self.stu_obs_mode], first[self.tea_obs_mode]
+
+    def _collect(self, stu_obs, tea_obs):
+        """n_steps of the student acting with exploration noise; every visited (student obs, teacher obs) pair enters the ring."""
+        episode = []
+        for _ in range(self.n_steps):
+            actions = self.student.random_act(stu_obs)
+            nxt, rews, _, infos = self.vec_env.step(actions)
+            self.storage.add_transitions_dagger(stu_obs, tea_obs)
+            episode.append(deepcopy(_action_summaries(infos, actions)))
+            stu_obs, tea_obs = nxt[self.stu_obs_mode], nxt[self.tea_obs_mode]
+            if self.reward_reset:                                   # dagger.py:228-233: restart envs that fall behind the teacher
+                prog = self.vec_env.progress_buf
+                self.vec_env.dagger_reward_reset = (prog > _REWARD_RESET_LAG) & (rews < self.tea_rew[prog - _REWARD_RESET_LAG])
+        return stu_obs, tea_obs, episode
 
     def run(self):
         if self.test_only:
             self.eval()
             self.logger.info(self.log_dict, self.curr_iter)
             return
-        all_curr_obs = self.vec_env.reset()
-        tea_curr_obs = all_curr_obs[self.tea_obs_mode]
-        stu_curr_obs = all_curr_obs[self.stu_obs_mode]
+        stu_obs, tea_obs = self._reset_env()
         while self.curr_iter < self.max_iter:
             self.curr_iter += 1
             self.student.train()
             self.teacher.eval()
             self.log_dict = {}
-            ep_infos = []
-            start = time.time()
-            for i in range(self.n_steps):
-                actions = self.student.random_act(stu_curr_obs)
-                next_obs, rews, dones, infos = self.vec_env.step(actions)
-                self.storage.add_transitions_dagger(stu_curr_obs, tea_curr_obs)
-                infos['action_t'] = actions[:, :3].mean(dim=-1)
-                infos['action_r'] = actions[:, 3:6].mean(dim=-1)
-                infos['action_gripper'] = actions[:, -1]
-                tea_curr_obs = next_obs[self.tea_obs_mode]
-                stu_curr_obs = next_obs[self.stu_obs_mode]
-                ep_infos.append(deepcopy(infos))
-                if self.reward_reset:   # dagger.py:228-233
-                    delta_step = 10
-                    self.vec_env.dagger_reward_reset = (self.vec_env.progress_buf > delta_step) & (
-                        rews < self.tea_rew[self.vec_env.progress_buf - delta_step])
+            t0 = time.time()
+            stu_obs, tea_obs, episode = self._collect(stu_obs, tea_obs)
             torch.cuda.synchronize()
-            collection_time = time.time() - start
-            start = time.time()
+            t1 = time.time()
             self.update(self.curr_iter)
             torch.cuda.synchronize()
-            learn_time = time.time() - start
-            self.total_envsteps += self.n_steps * self.vec_env.num_envs
+            collection_time, learn_time = t1 - t0, time.time() - t1
+            steps = self.n_steps * self.vec_env.num_envs
+            self.total_envsteps += steps
             self.total_time += collection_time + learn_time
-            self.log_dict['Progress/total_steps'] = self.curr_iter
-            self.log_dict['Progress/collection_time'] = collection_time
-            self.log_dict['Progress/learn_time'] = learn_time
-            self.log_dict['Progress/FPS'] = int(self.n_steps * self.vec_env.num_envs / (collection_time + learn_time))
-            self.log_dict['Train/mean_action_noise_std'] = self.student.log_std.detach().exp().mean().item()
-            self.log_dict['Train/cur_buf_size'] = self.storage.cur_buf_size
-            self.log_dict['Train/succ_buf_ind'] = self.storage.succ_buf_ind
-            self.log_dict['Train/mix_buf_ind'] = self.storage.mix_buf_ind
-            self.use_info_update_logdict(ep_infos, 'Train')
+            self.log_dict.update({
+                'Progress/total_steps': self.curr_iter,
+                'Progress/collection_time': collection_time,
+                'Progress/learn_time': learn_time,
+                'Progress/FPS': int(steps / (collection_time + learn_time)),
+                'Train/mean_action_noise_std': self.student.log_std.detach().exp().mean().item(),
+                'Train/cur_buf_size': self.storage.cur_buf_size,
+                'Train/succ_buf_ind': self.storage.succ_buf_ind,
+                'Train/mix_buf_ind': self.storage.mix_buf_ind,
+            })
+            self.use_info_update_logdict(episode, 'Train')
             if self.curr_iter % self.eval_freq == 0:
                 self.eval()
-                all_curr_obs = self.vec_env.reset()
-                tea_curr_obs = all_curr_obs[self.tea_obs_mode]
-                stu_curr_obs = all_curr_obs[self.stu_obs_mode]
+                stu_obs, tea_obs = self._reset_env()
             if self.curr_iter % self.save_freq == 0:
                 self.save(self.curr_iter)
             self.logger.info(self.log_dict, self.curr_iter)
 
     def use_info_update_logdict(self, info_lst, mode):
-        """dagger.py:280-297."""
-        for key in info_lst[0].keys():
-            assert len(info_lst[0][key].shape) == 1, f"{key}: {info_lst[0][key].shape}"
-            all_info = torch.stack([info[key].float() for info in info_lst], dim=-1)
-            if mode != 'Train':
-                self.log_dict.setdefault(f'{mode}/{key}_mean', 0)
-                self.log_dict.setdefault(f'{mode}/{key}_max', 0)
-                self.log_dict[f'{mode}/{key}_mean'] += torch.mean(all_info) / self.eval_round
-                self.log_dict[f'{mode}/{key}_max'] += torch.mean(all_info.max(dim=-1)[0]) / self.eval_round
-            else:
-                self.log_dict[f'{mode}/{key}_mean'] = torch.mean(all_info)
-                self.log_dict[f'{mode}/{key}_max'] = torch.mean(all_info.max(dim=-1)[0])
+        """dagger.py:280-297: per-key mean and mean-of-per-env-max over the episode; evaluation rounds are averaged."""
+        running = mode != 'Train'
+        for key, first in info_lst[0].items():
+            assert first.dim() == 1, f"{key}: {first.shape}"
+            series = torch.stack([step[key].float() for step in info_lst], dim=-1)          # (num_envs, steps)
+            for suffix, value in (('mean', series.mean()), ('max', series.max(dim=-1)[0].mean())):
+                name = f'{mode}/{key}_{suffix}'
+                self.log_dict[name] = self.log_dict.get(name, 0) + value / self.eval_round if running else value
 
+    # ------------------------------------------------------------------ the update (dagger.py:299-337)
     def _gather(self, src, indices, tag):
         if hasattr(indices, 'start'):
             return src[indices.start:indices.stop]
