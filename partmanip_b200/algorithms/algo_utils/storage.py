@@ -28,64 +28,55 @@ class _Range:
         return range(self.start, self.stop)[i]
 
 
+# PPO rollout fields (storage.py:28-41): name -> (trailing width: 'obs' / 'act' / 1, dtype)
+_PPO_FIELDS = {"observations": ("obs", torch.float32), "rewards": (1, torch.float32), "actions": ("act", torch.float32),
+               "dones": (1, torch.bool), "succs": (1, torch.bool), "actions_log_prob": (1, torch.float32),
+               "values": (1, torch.float32), "returns": (1, torch.float32), "advantages": (1, torch.float32),
+               "mu": ("act", torch.float32), "sigma": ("act", torch.float32), "step_id": (1, torch.float32)}
+
+
 class RolloutStorage:
 
     def __init__(self, num_envs, n_steps, obs_shape, actions_shape, device, default_succ_value=0, whole_adv_norm=False,
                  sampler='sequential', tea_obs_shape=None, max_length=None):
-        self.device = device
-        self.sampler = sampler
-        self.n_steps = n_steps
-        self.num_envs = num_envs
-        self.step = 0
-        self.whole_adv_norm = whole_adv_norm
+        self.device, self.sampler = device, sampler
+        self.n_steps, self.num_envs = n_steps, num_envs
+        self.whole_adv_norm, self.default_succ_value = whole_adv_norm, default_succ_value
         self.max_episode_length = max_length
         self.first_fill = True
-        self.default_succ_value = default_succ_value
-        z = lambda *s, **k: torch.zeros(*s, device=self.device, **k)
-        if tea_obs_shape is not None:   # DAgger ring buffer (storage.py:20-27)
-            self.tea_obs = z(self.n_steps * self.num_envs, tea_obs_shape)
-            self.observations = z(self.n_steps * self.num_envs, obs_shape)
-            self.succ_flag = z(self.n_steps * self.num_envs, 1)
-            self.mix_buf_ind = 0
-            self.succ_buf_ind = (self.max_episode_length or 0) * self.num_envs
-            self.cur_buf_size = 0
-            self.last_episode_buf_ind = 0
-        else:                           # PPO (storage.py:28-41)
-            self.observations = z(self.n_steps, num_envs, obs_shape)
-            self.rewards = z(self.n_steps, num_envs, 1)
-            self.cur_buf_size = self.n_steps * self.num_envs
-            self.actions = z(self.n_steps, num_envs, actions_shape)
-            self.dones = z(self.n_steps, num_envs, 1).bool()
-            self.succs = z(self.n_steps, num_envs, 1).bool()
-            self.actions_log_prob = z(self.n_steps, num_envs, 1)
-            self.values = z(self.n_steps, num_envs, 1)
-            self.returns = z(self.n_steps, num_envs, 1)
-            self.advantages = z(self.n_steps, num_envs, 1)
-            self.mu = z(self.n_steps, num_envs, actions_shape)
-            self.sigma = z(self.n_steps, num_envs, actions_shape)
-            self.step_id = z(self.n_steps, num_envs, 1)
+        self.step = 0
+        rows = n_steps * num_envs
+        if tea_obs_shape is not None:   # DAgger ring buffer (storage.py:20-27): flat (rows, .) arrays + ring cursors
+            for name, width in (("tea_obs", tea_obs_shape), ("observations", obs_shape), ("succ_flag", 1)):
+                setattr(self, name, torch.zeros(rows, width, device=device))
+            self.mix_buf_ind = self.cur_buf_size = self.last_episode_buf_ind = 0
+            self.succ_buf_ind = (max_length or 0) * num_envs
+        else:                           # PPO (storage.py:28-41): (T, E, .) arrays, always full
+            widths = {"obs": obs_shape, "act": actions_shape, 1: 1}
+            for name, (w, dtype) in _PPO_FIELDS.items():
+                setattr(self, name, torch.zeros(n_steps, num_envs, widths[w], device=device, dtype=dtype))
+            self.cur_buf_size = rows
+
+    def _slot_index(self):
+        if self.step >= self.n_steps:
+            raise AssertionError("Rollout buffer overflow")
+        return self.step
 
     def obs_slot(self):
         """The (E, D) view the next add_transitions will fill — producers may write into it directly."""
-        if self.step >= self.n_steps:
-            raise AssertionError("Rollout buffer overflow")
-        return self.observations[self.step]
+        return self.observations[self._slot_index()]
 
     def add_transitions(self, observations, actions, rewards, dones, succs, values, actions_log_prob, mu, sigma):
-        if self.step >= self.n_steps:
-            raise AssertionError("Rollout buffer overflow")
-        slot = self.observations[self.step]
+        t = self._slot_index()
+        slot = self.observations[t]
         if observations.data_ptr() != slot.data_ptr():          # already produced in place: nothing to move
             ops.copy_rows(observations, slot)
-        self.actions[self.step].copy_(actions)
-        self.rewards[self.step].copy_(rewards.view(-1, 1))
-        self.dones[self.step].copy_(dones.view(-1, 1))
-        self.succs[self.step].copy_(succs.view(-1, 1))
-        self.values[self.step].copy_(values.view(-1, 1))
-        self.actions_log_prob[self.step].copy_(actions_log_prob.view(-1, 1))
-        self.mu[self.step].copy_(mu)
-        self.sigma[self.step].copy_(sigma)
-        self.step = self.step + 1
+        per_env = dict(rewards=rewards, dones=dones, succs=succs, values=values, actions_log_prob=actions_log_prob)
+        for name, column in per_env.items():                    # (E,) or (E,1) producers -> the (E,1) slot
+            getattr(self, name)[t].copy_(column.view(-1, 1))
+        for name, block in (("actions", actions), ("mu", mu), ("sigma", sigma)):
+            getattr(self, name)[t].copy_(block)
+        self.step = t + 1
 
     def add_transitions_dagger(self, stu_obs, tea_obs):
         """storage.py:84-91."""
