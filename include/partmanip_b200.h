@@ -56,6 +56,12 @@ const char* pm_last_error(void);
 int pm_version(void);
 /* 1 if the tcgen05 (sm_100a) encoder path was compiled in */
 int pm_has_tcgen05(void);
+/* The tcgen05 kernels bound every mbarrier wait; a wait that times out (protocol bug, or a pathologically slow device) records
+ * its code in a per-device word that no launch clears.  Returns the first code since the last clear on the CURRENT device
+ * (0 = none) and clears it when clear != 0.  Synchronises the device.  The algorithm classes call it once per iteration and
+ * raise: features / gradients of a launch that reported an error are garbage (the reference has no equivalent: PyTorch
+ * kernels cannot time out). */
+int pm_tc_sticky_error(int clear);
 
 /* ------------------------------------------------------------------------------------------
  * K6  running mean / std observation normaliser

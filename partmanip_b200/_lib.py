@@ -27,6 +27,7 @@ SIGNATURES = {
     "pm_last_error": (C.c_char_p, []),
     "pm_version": (I, []),
     "pm_has_tcgen05": (I, []),
+    "pm_tc_sticky_error": (I, [I]),
     "pm_colreduce_ws_bytes": (SZ, [I, I]),
     "pm_rms_colsum": (I, [P, L, I, I, P, P, P]),
     "pm_rms_colsqdev": (I, [P, L, I, I, P, F, P, P, P]),

@@ -38,12 +38,21 @@ class ActorCritic(nn.Module):
         if self.action_activate not in ('tanh', None):
             raise NotImplementedError
         self.num_actions = actions_shape
-        # counter-based RNG state for pm_randn (Philox): (seed, offset)
-        self._seed = int(torch.initial_seed()) & (2 ** 63 - 1)
+        # counter-based RNG state for pm_randn (Philox): (seed, offset).  The rank is mixed into the key so that env shards on
+        # different GPUs draw independent exploration noise when every rank calls torch.manual_seed(seed) (the usual set_seed)
+        from ... import parallel
+        self._seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * parallel.rank()) & (2 ** 63 - 1)
         self._offset = 0
         # flat buffers (set by flatten_())
         self.actor_flat: Optional[torch.Tensor] = None
         self.critic_flat: Optional[torch.Tensor] = None
+
+    def rng_state(self) -> dict:
+        """Philox (seed, offset) — saved with checkpoints so that a resumed run continues the noise sequence."""
+        return {'seed': self._seed, 'offset': self._offset}
+
+    def set_rng_state(self, st: dict):
+        self._seed, self._offset = int(st['seed']), int(st['offset'])
 
     # ------------------------------------------------------------------ flat parameter storage
     def flatten_(self):

@@ -114,15 +114,24 @@ class RolloutStorage:
 
 
 class _RandomBatches:
-    """SubsetRandomSampler + BatchSampler(drop_last=True): a fresh permutation on every iteration."""
+    """SubsetRandomSampler + BatchSampler(drop_last=True) (storage.py:133-137): a fresh permutation on every iteration.
+
+    The permutation is drawn exactly where the reference draws it — `torch.randperm(n)` on the HOST default generator
+    (torch.utils.data.SubsetRandomSampler.__iter__) — so that for a given `torch.manual_seed` every minibatch holds the rows
+    the reference's holds; one pinned, asynchronous copy moves the n indices to the device."""
 
     def __init__(self, n, size, count, device):
         self.n, self.size, self.count, self.device = n, size, count, device
+        self._pinned = torch.empty(n, dtype=torch.int64).pin_memory() if str(device).startswith("cuda") else None
 
     def __len__(self):
         return self.count
 
     def __iter__(self):
-        perm = torch.randperm(self.n, device=self.device)
+        perm = torch.randperm(self.n)
+        if self._pinned is not None:
+            torch.cuda.current_stream().synchronize()      # the previous epoch's copy out of the pinned buffer has finished
+            self._pinned.copy_(perm)
+            perm = self._pinned.to(self.device, non_blocking=True)
         for k in range(self.count):
-            yield perm[k * self.size:(k + 1) * self.size].contiguous()
+            yield perm[k * self.size:(k + 1) * self.size]

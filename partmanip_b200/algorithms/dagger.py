@@ -18,7 +18,7 @@ import torch
 
 from .. import ops
 from .algo_utils import ActorCritic, RolloutStorage
-from .ppo import FlatAdam
+from .ppo import FlatAdam, _path2video
 
 # attribute <- cfg key (dagger.py:18-51); the attribute names are the reference's, other code reads them
 _CFG_ATTRS = (("num_envs", "num_envs"), ("stu_obs_mode", "obs_mode"), ("model_cfg", "model"), ("max_iter", "max_iterations"),
@@ -64,13 +64,15 @@ class dagger:
         self._mb = {}
 
     def _build_student(self, proprio_dim):
-        """dagger.py:53-56: one Adam over all student parameters.  Only the actor ever receives a gradient and torch's Adam skips
-        grad-less tensors, so the flat optimiser covers exactly the actor block."""
+        """dagger.py:53-56: one Adam over all student parameters, in `student.parameters()` order [log_std, actor.*, critic.*].
+        Only the actor ever receives a gradient and torch's Adam skips grad-less tensors, so the flat optimiser steps exactly
+        the actor block; its state_dict keeps the reference's indices (actor tensors at 1..n, one group over all tensors)."""
         self.student = ActorCritic(self.stu_input_obs, self.num_actions, self.model_cfg, proprio_dim).to(self.device)
         flat = self.student.flatten_()
         tensors = list(flat.actor.parameters())
         offsets = flat.actor_offs[:-1]
-        self.optimizer = FlatAdam(flat.actor_flat[:flat.actor_n_clip], tensors, offsets, [len(tensors)], self.lr, 0, 0.0)
+        self.optimizer = FlatAdam(flat.actor_flat[:flat.actor_n_clip], tensors, offsets, [len(tensors)], self.lr, 0, 0.0,
+                                  index_offset=1, n_unstepped_tail=len(list(flat.critic.parameters())))
         self._grads = [self.optimizer.grad[o:o + t.numel()].view(t.shape) for t, o in zip(tensors, offsets)]
 
     def _load_teacher(self):
@@ -90,7 +92,8 @@ class dagger:
         target = pjoin(self.save_ckpt_dir, f'model_{it}.pth')
         weights = {name: t.detach().clone() for name, t in self.student.state_dict().items()}
         torch.save(dict(iteration=it, model_state_dict=weights, optimizer_state_dict=self.optimizer.state_dict(),
-                        total_steps=self.total_envsteps, obs_mode=self.stu_obs_mode, teacher=self.teacher_path), target)
+                        total_steps=self.total_envsteps, obs_mode=self.stu_obs_mode, teacher=self.teacher_path,
+                        b200_rng=self.student.rng_state()), target)
         print(f'save ckpt to {target}!')
 
     def _read_ckpt(self, ckpt_path):
@@ -111,6 +114,8 @@ class dagger:
         self.student.load_state_dict(ckpt["model_state_dict"])
         self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
         self.curr_iter, self.total_envsteps = ckpt["iteration"], ckpt["total_steps"]
+        if 'b200_rng' in ckpt:
+            self.student.set_rng_state(ckpt['b200_rng'])
 
     # ------------------------------------------------------------------ evaluation (dagger.py:114-178)
     def eval(self):
@@ -118,8 +123,8 @@ class dagger:
         if self.test_only:
             self.log_dict = {}
         mode = 'Test' if self.test_only else 'Val'
-        for _ in range(self.eval_round):
-            episode = []
+        for r in range(self.eval_round):
+            episode, poses = [], []
             obs = self.vec_env.reset()[self.stu_obs_mode]
             for t in range(self.max_episode_length):
                 actions = self.student.act(obs)
@@ -127,7 +132,17 @@ class dagger:
                 nxt, rews, _, infos = self.vec_env.step(actions, save_image_path=frame)
                 _action_summaries(infos, actions)['reward'] = rews
                 episode.append(deepcopy(infos))
+                if self.save_pose:                                  # dagger.py:155-159
+                    rec = self.vec_env.save_scene_pose(pjoin(self.logger.save_pose_dir, f"Iter{self.curr_iter}", f"{t}.npy"))
+                    rec['state'], rec['action'] = obs.cpu().numpy(), actions.cpu().numpy()
+                    poses.append(deepcopy(rec))
                 obs = nxt[self.stu_obs_mode]
+            if self.save_pose:                                      # dagger.py:163-167
+                for t, rec in enumerate(poses):
+                    rec['success'] = episode[-1]['obj_up_flag'].cpu().numpy()
+                    np.save(pjoin(self.logger.save_pose_dir, f"Iter{self.curr_iter}", f"{t}.npy"), rec)
+            if self.save_video and r == self.eval_round - 1:        # dagger.py:169-171
+                _path2video()(pjoin(self.logger.save_video_dir, f"Iter{self.curr_iter}"))
             self.use_info_update_logdict(episode, mode)
 
     # ------------------------------------------------------------------ training loop (dagger.py:180-278)
@@ -234,6 +249,7 @@ class dagger:
                 self.optimizer.step(None)
                 count += 1
         mean_loss = self._acc[0].item() / max(count, 1)
+        ops.check_tc_errors()
         if self.lr_schedule == 'linear_decay':
             self.optimizer.set_lr(self.lr * max(1 - it / self.max_iter * 1.8, 0.1))
         elif self.lr_schedule != 'fixed':

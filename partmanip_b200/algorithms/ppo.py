@@ -26,13 +26,28 @@ from .. import ops, parallel
 from .algo_utils import ActorCritic, Normalization, RolloutStorage
 
 
+def _path2video():
+    """The reference's frame-folder -> video helper (`from utils import path2video`, ppo.py:1; cv2 + ffmpeg, outside the hot
+    path).  Resolved lazily from the host project's `utils` package so that `save_video: True` keeps working when this
+    class is dropped into the reference tree, and fails loudly (instead of silently skipping the step) elsewhere."""
+    try:
+        from utils import path2video
+    except Exception as e:  # pragma: no cover - depends on the host project
+        raise NotImplementedError("save_video needs the host project's utils.path2video (cv2/ffmpeg): %s" % (e,))
+    return path2video
+
+
 class FlatAdam:
     """torch.optim.Adam (defaults: betas (0.9, 0.999), eps 1e-8, no weight decay) over one flat buffer, stepped by
     pm_adam_step.  state_dict()/load_state_dict() speak torch.optim's format so reference checkpoints round-trip
     (ppo.py:89-90, 121-122)."""
 
-    def __init__(self, flat, params, offsets, group_sizes, lr, n_clip, max_norm):
+    def __init__(self, flat, params, offsets, group_sizes, lr, n_clip, max_norm, index_offset=0, n_unstepped_tail=0):
+        """`index_offset` / `n_unstepped_tail`: parameters of the reference optimiser that sit before / after this buffer's
+        tensors in `module.parameters()` order and never receive a gradient (DAgger: log_std before, the critic after —
+        dagger.py:56); they shift the state indices and widen param_groups[0]['params'] so the dict is torch.optim.Adam's."""
         self.flat, self.params, self.offsets, self.group_sizes = flat, params, offsets, group_sizes
+        self.index_offset, self.n_unstepped_tail = int(index_offset), int(n_unstepped_tail)
         # gradient buffer with a 4-float tail: per-step scalars that must be summed over ranks (sum surrogate, sum KL) ride
         # in the SAME all-reduce as the gradients (one collective per optimiser step)
         self.grad_ext = torch.zeros(flat.numel() + 4, device=flat.device, dtype=torch.float32)
@@ -69,9 +84,12 @@ class FlatAdam:
         state = {}
         if float(step) > 0:
             for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
-                state[i] = {'step': step.clone(), 'exp_avg': m.clone(), 'exp_avg_sq': v.clone()}
+                state[i + self.index_offset] = {'step': step.clone(), 'exp_avg': m.clone(), 'exp_avg_sq': v.clone()}
         groups, k = [], 0
-        for g, n in zip(self.param_groups, self.group_sizes):
+        sizes = list(self.group_sizes)
+        sizes[0] += self.index_offset
+        sizes[-1] += self.n_unstepped_tail
+        for g, n in zip(self.param_groups, sizes):
             groups.append({'lr': g['lr'], 'betas': (0.9, 0.999), 'eps': 1e-08, 'weight_decay': 0, 'amsgrad': False,
                            'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False,
                            'fused': None, 'params': list(range(k, k + n))})
@@ -81,11 +99,18 @@ class FlatAdam:
     def load_state_dict(self, sd):
         st = sd['state']
         steps = []
+        n_ref = sum(len(g['params']) for g in sd['param_groups'])
+        n_here = len(self.params) + self.index_offset + self.n_unstepped_tail
+        if n_ref != n_here:
+            raise ValueError(f"optimizer state_dict covers {n_ref} parameters, this optimiser {n_here}")
         for i, (m, v) in enumerate(zip(self._views(self.exp_avg), self._views(self.exp_avg_sq))):
-            if i in st:
-                m.copy_(st[i]['exp_avg'])
-                v.copy_(st[i]['exp_avg_sq'])
-                steps.append(float(st[i]['step']))
+            j = i + self.index_offset
+            if j in st:
+                if tuple(st[j]['exp_avg'].shape) != tuple(m.shape):
+                    raise ValueError(f"optimizer state {j}: shape {tuple(st[j]['exp_avg'].shape)} != {tuple(m.shape)}")
+                m.copy_(st[j]['exp_avg'])
+                v.copy_(st[j]['exp_avg_sq'])
+                steps.append(float(st[j]['step']))
         # one step counter per flat buffer: the reference's two param groups always step together
         self.opt_state[0:1].fill_(max(steps) if steps else 0.0)
         self._lr_on_device = None
@@ -194,6 +219,7 @@ class ppo:
             'tricks': self.tricks,
             'obs_mode': self.obs_mode,
             'model_cfg': self.model_cfg,
+            'b200_rng': self.actor_critic.rng_state(),      # extra key (the reference ignores unknown keys)
         }
         if self.tricks['use_state_norm']:
             save_dict['state_running_ms'] = self.state_norm.running_ms.save()
@@ -212,6 +238,8 @@ class ppo:
         self.optimizer_critic.load_state_dict(ckpt_dict["optimizer_critic"])
         self.curr_iter = ckpt_dict["iteration"]
         self.total_envsteps = ckpt_dict["total_steps"]
+        if 'b200_rng' in ckpt_dict:                         # absent in reference-written checkpoints
+            self.actor_critic.set_rng_state(ckpt_dict['b200_rng'])
         for k in self.tricks_keys:
             if self.tricks[k] != ckpt_dict['tricks'][k]:
                 print(f"WARNING: trick {k} is not consistent with ckpt! saved: {ckpt_dict['tricks'][k]}, now: {self.tricks[k]}")
@@ -230,6 +258,7 @@ class ppo:
             self.log_dict = {}
         ep_infos = []
         for r in range(self.eval_round):
+            save_dict_lst = []
             curr_obs = self.vec_env.reset()[self.obs_mode]
             for i in range(self.max_episode_length):
                 if self.tricks['use_state_norm']:
@@ -243,7 +272,18 @@ class ppo:
                 infos['action_gripper'] = actions[:, -1]
                 infos['succ_rate'] = self.vec_env.success
                 ep_infos.append(deepcopy(infos))
+                if self.save_pose:                                  # ppo.py:177-181 (host-side bookkeeping of the env's scene)
+                    save_dict = self.vec_env.save_scene_pose(pjoin(self.logger.save_pose_dir, f"Iter{self.curr_iter}", f"{i}.npy"))
+                    save_dict['state'] = curr_obs.cpu().numpy()
+                    save_dict['action'] = actions.cpu().numpy()
+                    save_dict_lst.append(deepcopy(save_dict))
                 curr_obs = next_obs[self.obs_mode]
+            if self.save_pose:                                      # ppo.py:185-189
+                for i in range(self.max_episode_length):
+                    save_dict_lst[i]['success'] = ep_infos[-1]['obj_up_flag'].cpu().numpy()
+                    np.save(pjoin(self.logger.save_pose_dir, f"Iter{self.curr_iter}", f"{i}.npy"), save_dict_lst[i])
+            if self.save_video:                                     # ppo.py:191-193
+                _path2video()(pjoin(self.logger.save_video_dir, f"Iter{self.curr_iter}"))
         mode = 'Test' if self.test_only else 'Val'
         self.use_info_update_logdict(ep_infos, mode)
         if self.log_dict[f'{mode}/succ_rate_max'] > 0.5 and getattr(self, 'update_RMS', False):
@@ -425,6 +465,11 @@ class ppo:
     def update(self, it):
         if not self.cuda_graph:
             self._update_body()
+        elif self._graph is not None and self._graph_scratch_gen != ops.scratch_generation():
+            # a workspace the captured kernels point into was re-allocated (another runner / a larger batch grew it): the
+            # graph holds dangling pointers — drop it and start over (eager now, re-capture on the next call)
+            self._graph, self._graph_calls = None, 0
+            self._update_body()
         elif self._graph is not None:
             self._graph.replay()
             ops.count_launches(self._graph_launches)      # the replay launches the same kernels the capture recorded
@@ -438,11 +483,13 @@ class ppo:
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 self._update_body()
             self._graph, self._graph_launches = graph, ops.launch_count() - n0
+            self._graph_scratch_gen = ops.scratch_generation()
             graph.replay()
         self._graph_calls += 1
         n_critic = self._n_critic
         # ---- one read-back per iteration
         acc = self._acc.tolist()
+        ops.check_tc_errors()
         count = int(round(acc[2]))
         mean_value_loss = acc[4] / max(n_critic, 1)
         if count == 0:

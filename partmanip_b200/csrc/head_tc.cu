@@ -67,7 +67,7 @@ constexpr uint32_t F_A = 0, F_B = 32768, F_H1 = 65536, F_W1 = 98304, F_W2 = 1064
 template <int ACT>
 __global__ void __launch_bounds__(GT, 1)
 head_fwd_tc_kernel(const float* __restrict__ feat, int64_t ldf, int B, int F, pm_head_params P, int out_dim,
-                   float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ out, int64_t ldo, int32_t* __restrict__ err) {
+                   float* __restrict__ h1, float* __restrict__ h2, float* __restrict__ out, int64_t ldo, ErrSink err) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -185,7 +185,7 @@ constexpr uint32_t D_A = 0, D_B = 32768, D_BAR = 98304, D_TOTAL = 98304 + 64;
 
 __global__ void __launch_bounds__(GT, 1)
 head_dfeat_tc_kernel(const float* __restrict__ dpre1, int B, const float* __restrict__ W0, int F, float* __restrict__ dfeat,
-                     int64_t lddf, int dfeat_cols, int32_t* __restrict__ err) {
+                     int64_t lddf, int dfeat_cols, ErrSink err) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -241,7 +241,7 @@ head_dfeat_tc_kernel(const float* __restrict__ dpre1, int B, const float* __rest
 // grid (column tiles of 256, row slabs of 128).  smem: A = dPre1 slab as 2 MN blocks (32 KB) | B = feat slab as 4 MN blocks (64 KB)
 __global__ void __launch_bounds__(GT, 1)
 head_dw0_tc_kernel(const float* __restrict__ dpre1, const float* __restrict__ feat, int64_t ldf, int B, int F,
-                   float* __restrict__ part, int32_t* __restrict__ err) {
+                   float* __restrict__ part, ErrSink err) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -291,7 +291,8 @@ extern "C" {
 
 // launched by head.cu's entry points when precision == PM_PREC_BF16
 int pm_head_fwd_tc_launch(const float* feat, int64_t ldf, int B, int F, const pm_head_params* p, int out_dim, int act, float* h1,
-                          float* h2, float* out, int64_t ldo, int32_t* err, cudaStream_t st) {
+                          float* h2, float* out, int64_t ldo, int32_t* err_word, cudaStream_t st) {
+  const ErrSink err{err_word, pm_tc_sticky_word()};
   const dim3 grid(pm_cdiv(B, 128));
 #define PM_HTF(ACTV)                                                                                                     \
   case ACTV: {                                                                                                           \
@@ -313,7 +314,8 @@ int pm_head_fwd_tc_launch(const float* feat, int64_t ldf, int B, int F, const pm
 }
 
 int pm_head_bwd_tc_launch(const float* dpre1, const float* feat, int64_t ldf, int B, int F, const float* W0, float* dfeat,
-                          int64_t lddf, int dfeat_cols, float* partB, int32_t* err, cudaStream_t st) {
+                          int64_t lddf, int dfeat_cols, float* partB, int32_t* err_word, cudaStream_t st) {
+  const ErrSink err{err_word, pm_tc_sticky_word()};
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e1 = cudaFuncSetAttribute(head_dfeat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_TOTAL);

@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, const int32_t* __restrict__ argmax,
                const float* __restrict__ dfeat, int64_t lddf, const uint8_t* __restrict__ w2img,
                const uint32_t* __restrict__ w3pack, const float* __restrict__ W1, const float* __restrict__ b1,
-               const float* __restrict__ b2, float* __restrict__ part_all, int32_t* __restrict__ err) {
+               const float* __restrict__ b2, float* __restrict__ part_all, ErrSink err) {
 #ifdef PM_TC_TIMING
-  long long* dbg = reinterpret_cast<long long*>(err + 16);
+  long long* dbg = reinterpret_cast<long long*>(err.last + 16);
 #define BSTAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && it == 3) dbg[(slot)] = clock64(); } while (0)
 #else
 #define BSTAMP(slot) do { } while (0)
@@ -121,7 +121,7 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   auto bar = [&](int i) { return sbase + SB_BAR + 8u * i; };
 
   // ---------------- prologue
-  if ((sbase & 1023u) != 0 && tid == 0) atomicExch(err, 900);
+  if ((sbase & 1023u) != 0 && tid == 0) err_report(err, 900);
   {
     const uint4* src = reinterpret_cast<const uint4*>(w2img);
     uint4* dst = reinterpret_cast<uint4*>(smem + SB_W2);
@@ -510,6 +510,7 @@ int pm_pointnet_encode_backward_tc(const float* x, int64_t ldx, int B, int N, in
   int32_t* err = reinterpret_cast<int32_t*>(w2img + W2IMG_BYTES + W3PACK_BYTES);
   float* part = reinterpret_cast<float*>(w2img + W2IMG_BYTES + W3PACK_BYTES + 4096);
   cudaMemsetAsync(err, 0, sizeof(int32_t), st);
+  const ErrSink sink{err, pm_tc_sticky_word()};
   pack_bwd_weights_kernel<<<64, 256, 0, st>>>(p->W2, p->W3, w2img, w3pack);
   const int G = bwd_grid(B);
 #define PM_BT_LAUNCH(ACTV)                                                                                                  \
@@ -521,7 +522,7 @@ int pm_pointnet_encode_backward_tc(const float* x, int64_t ldx, int B, int N, in
       attr_set = true;                                                                                                      \
     }                                                                                                                       \
     encoder_bwd_tc<ACTV><<<G, BT_THREADS, SB_TOTAL, st>>>(x, ldx, B, N, C, argmax, dfeat, lddf, w2img, w3pack, p->W1, p->b1, \
-                                                          p->b2, part, err);                                               \
+                                                          p->b2, part, sink);                                               \
   } break;
   switch (act) {
     PM_BT_LAUNCH(PM_ACT_TANH)

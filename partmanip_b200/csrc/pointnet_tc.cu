@@ -141,9 +141,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, const uint8_t* __restrict__ wpack,
                const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ b2,
                const float* __restrict__ b3, float* __restrict__ feat, int64_t ldf,
-               int32_t* __restrict__ argmax, int32_t* __restrict__ err, uint8_t* __restrict__ scratch) {
+               int32_t* __restrict__ argmax, ErrSink err, uint8_t* __restrict__ scratch) {
 #ifdef PM_TC_TIMING
-  long long* dbg = reinterpret_cast<long long*>(err + 16);
+  long long* dbg = reinterpret_cast<long long*>(err.last + 16);
 #define TSTAMP(slot) do { if (blockIdx.x < 2 && it == 3) dbg[blockIdx.x * 64 + (slot)] = clock64(); } while (0)
 #else
 #define TSTAMP(slot) do { } while (0)
@@ -163,7 +163,7 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   auto tile_cloud = [&](int it) { return cluster_id + (it / tpc) * n_clusters; };
 
   // ---------------- prologue: resident weights, barriers, TMEM
-  if ((sbase & 1023u) != 0 && tid == 0) atomicExch(err, 900);
+  if ((sbase & 1023u) != 0 && tid == 0) err_report(err, 900);
   {
     const uint4* src = reinterpret_cast<const uint4*>(wpack + (size_t)rank * WPACK_PER_RANK);
     uint4* dst = reinterpret_cast<uint4*>(smem);
@@ -456,6 +456,7 @@ int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int
   uint8_t* wpack = reinterpret_cast<uint8_t*>(ws);
   int32_t* err = reinterpret_cast<int32_t*>(wpack + 2 * WPACK_PER_RANK);
   cudaMemsetAsync(err, 0, sizeof(int32_t), st);
+  const ErrSink sink{err, pm_tc_sticky_word()};
   pack_weights_kernel<<<64, 256, 0, st>>>(p->W2, p->W3, wpack);
   int n_clusters = B < PM_NUM_SMS / 2 ? B : PM_NUM_SMS / 2;
   dim3 grid(2 * n_clusters);
@@ -469,9 +470,9 @@ int pm_pointnet_encode_forward_tc(const float* x, int64_t ldx, int B, int N, int
       attr_set = true;                                                                                                      \
     }                                                                                                                       \
     if (argmax)                                                                                                             \
-      encoder_fwd_tc<ACTV, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, argmax, err, wpack + 2 * WPACK_PER_RANK + 4096); \
+      encoder_fwd_tc<ACTV, true><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, argmax, sink, wpack + 2 * WPACK_PER_RANK + 4096); \
     else                                                                                                                    \
-      encoder_fwd_tc<ACTV, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, nullptr, err, wpack + 2 * WPACK_PER_RANK + 4096); \
+      encoder_fwd_tc<ACTV, false><<<grid, TC_THREADS, SM_TOTAL, st>>>(x, ldx, B, N, C, wpack, p->W1, p->b1, p->b2, p->b3, feat, ldf, nullptr, sink, wpack + 2 * WPACK_PER_RANK + 4096); \
   } break;
   switch (act) {
     PM_TC_LAUNCH(PM_ACT_TANH)

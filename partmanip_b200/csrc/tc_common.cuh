@@ -3,6 +3,9 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 
+// library-owned sticky error word of the current device (api.cu); allocated on first use — call once outside graph capture
+int32_t* pm_tc_sticky_word();
+
 namespace pmtc {
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -25,12 +28,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // (plain try_wait / arrive as in cutlass::arch::ClusterBarrier: an `.acquire.cluster` qualifier makes ptxas emit
 // CCTL.IVALL — an L1 invalidate — on every spin; measured 12x slowdown of the whole kernel)
+// Where a tcgen05 kernel reports a protocol failure: `last` is the launch's own word inside the caller's workspace (cleared by
+// every launch; the *_last_error diagnostics read it), `sticky` a library-owned word per device that NO launch clears — the
+// algorithm classes read it once per iteration and raise, so a timed-out wait can never silently feed garbage to training.
+struct ErrSink {
+  int32_t* last;
+  int32_t* sticky;
+};
+__device__ __forceinline__ void err_report(const ErrSink& e, int code) {
+  if (e.last) atomicExch(e.last, code);
+  if (e.sticky) atomicCAS(e.sticky, 0, code);
+}
 // bounded wait: a protocol bug must surface as an error code, never as a hung GPU
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* err, int code) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, const ErrSink& err, int code) {
 #pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 22); ++spin)
     if (mbar_try_wait(bar, parity)) return true;
-  if (err) atomicExch(err, code);
+  err_report(err, code);
   return false;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t target_rank) {

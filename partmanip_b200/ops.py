@@ -54,6 +54,13 @@ def count_launches(n: int):
 
 
 _scratch = {}
+_scratch_gen = [0]
+
+
+def scratch_generation() -> int:
+    """Bumped whenever an EXISTING workspace is replaced by a larger one.  A captured CUDA graph bakes workspace pointers in;
+    its owner compares this counter with the value at capture time and re-captures when it moved (ppo.update)."""
+    return _scratch_gen[0]
 
 
 def scratch(nbytes: int, device, tag: str = "default") -> Tensor:
@@ -61,6 +68,11 @@ def scratch(nbytes: int, device, tag: str = "default") -> Tensor:
     key = (str(device), tag)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"workspace {tag!r} would be (re)allocated inside a CUDA-graph capture; run the same call "
+                               "eagerly once first")
+        if buf is not None:
+            _scratch_gen[0] += 1
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _scratch[key] = buf
     return buf
@@ -334,6 +346,16 @@ def pointnet_encode_forward(x: Tensor, N: int, C: int, enc_params: Sequence[Tens
     check(lib.pm_pointnet_encode_forward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], prec,
                                          _p(feat), _p(feat_mean), ldf, _p(argmax), _p(h2mean), _p(ws), nbytes, _stream()),
           "pm_pointnet_encode_forward")
+
+
+def check_tc_errors():
+    """Raise if any tcgen05 kernel on the current device reported a timed-out mbarrier wait since the last check (its outputs
+    are garbage).  One 4-byte read; the algorithm classes call it right after their once-per-iteration read-back."""
+    code = int(lib.pm_tc_sticky_error(1))
+    if code:
+        from ._lib import PMError
+        raise PMError(f"a tcgen05 kernel reported protocol error {code} (bounded mbarrier wait timed out): the results of this "
+                      "iteration are invalid")
 
 
 def pointnet_tc_last_error(device) -> int:

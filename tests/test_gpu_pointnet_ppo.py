@@ -159,10 +159,12 @@ class _Logger:
         self.last = d
 
 
-def _runner(name):
+def _runner(name, precision="fp32"):
     from partmanip_b200.algorithms import ppo
     g = load_golden(name)
     E, D, A, net, over = ITER_CASES[name]
+    if precision != "fp32":
+        net = dict(net, precision=precision)
     cfg = ppo_cfg(E, net, device=DEV, **over)
     env = _ReplayEnv(g, E, D, A)
     r = ppo(env, cfg, _Logger())
@@ -209,7 +211,7 @@ def test_full_iteration_against_reference_recording(name):
     # yardstick is the total displacement 40*lr.  The 40-step trajectory is CHAOTIC in the max-pool: a weight difference
     # of 1e-3*lr (fp32 summation order: MKL vs these kernels) flips the argmax between two near-tied points of some
     # cloud after a few steps, that row's gradient then differs by O(1e-2) and Adam amplifies it (measured in lockstep,
-    # scripts/dbg_iter3.py: two of OUR OWN kernel variants whose single-step gradients agree to 1e-7 drift apart by
+    # a lockstep debug run in round 1: two of OUR OWN kernel variants whose single-step gradients agree to 1e-7 drift apart by
     # 10*lr on the worst critic element after 40 steps, first flip at step 6).  Single-step gradient parity is gated
     # tightly elsewhere (test_pointnet_golden_backward, test_fused_head_*, test_encoder_backward_*: 1e-4); here the
     # gate is statistical: every element within half the displacement, >= 90 % of each tensor within 2 % of it, RMS
@@ -221,6 +223,82 @@ def test_full_iteration_against_reference_recording(name):
         assert float((d > 0.02 * disp).float().mean()) <= 0.10, (k, float((d > 0.02 * disp).float().mean()))
         assert float(d.pow(2).mean().sqrt()) <= 0.02 * disp, (k, float(d.pow(2).mean().sqrt()))
     assert math.isclose(float(sd["log_std"].exp().mean()), float(g["log.Train/mean_action_noise_std"]), rel_tol=1e-5)
+
+
+@pytest.mark.parametrize("name", [n for n, c in ITER_CASES.items() if c[3]["name"] == "PointNet"])
+def test_full_iteration_bf16_against_reference_recording(name):
+    """The BENCHMARKED mode (tcgen05, bf16 operands) through a whole recorded `ppo.run()` iteration of the unmodified reference
+    (algorithms/ppo.py:205-411): rollout outputs, GAE outputs, losses, KL and the skip count at north_star's bf16 gate
+    |a-b| <= 1e-2 + 1e-2*|b|."""
+    from partmanip_b200 import ops
+    g, cfg, env, r = _runner(name, "bf16")
+    gate = lambda a, b: close(a, b, 1e-2, 1e-2)
+    curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+    last_obs, last_values = r.collect(curr, None, eps=cu(g["eps"]))
+    ops.check_tc_errors()
+    st = r.storage
+    assert close(st.observations.cpu(), g["buf.observations"], 1e-4, 1e-4)            # the normaliser stays fp32
+    for k in ("mu", "actions", "actions_log_prob", "values"):
+        got, want = getattr(st, k).cpu(), g["buf." + k]
+        assert gate(got, want), (k, max_err(got, want))
+    assert torch.equal(st.sigma.cpu(), g["buf.sigma"]) and torch.equal(st.dones.cpu(), g["buf.dones"])
+    st.compute_returns(last_values, cfg["gamma"], cfg["lam"])
+    assert gate(st.returns.cpu(), g["buf.returns"]), max_err(st.returns.cpu(), g["buf.returns"])
+    assert gate(st.advantages.cpu(), g["buf.advantages"]), max_err(st.advantages.cpu(), g["buf.advantages"])
+    # ---- update from the reference's exact buffer (isolates the update kernels, as in the fp32 test)
+    for k in ("observations", "actions", "values", "returns", "advantages", "actions_log_prob", "mu", "sigma"):
+        getattr(st, k).copy_(cu(g["buf." + k]))
+    r.update(1)
+    log = r.log_dict
+    assert log["Train/kl_update_count"] == int(g["log.Train/kl_update_count"])
+    assert r.optimizer_actor.step_count == int(g["adam_actor.0.step"])
+    assert r.optimizer_critic.step_count == int(g["adam_critic.0.step"])
+    for k in ("Train/surrogate_loss", "Train/value_function_loss", "Train/kl", "Train/kl_max"):
+        assert gate(log[k], g["log." + k]), (k, float(log[k]), float(g["log." + k]))
+    # post-update weights: every element moved by at most the 40-step Adam displacement, and the bulk follows the reference's
+    # trajectory (bf16 gradients agree with fp32 ones to ~3e-3 relative L2; Adam's m/sqrt(v) keeps the per-step error at that
+    # fraction of lr for all but the near-zero-gradient elements)
+    disp = 40 * cfg["lr"]
+    sd = {k: v.cpu() for k, v in r.actor_critic.state_dict().items()}
+    worst = 0.0
+    for k, v in sub(g, "final").items():
+        d = (sd[k] - v).abs()
+        assert float(d.max()) <= disp, (k, float(d.max()))
+        worst = max(worst, float(d.pow(2).mean().sqrt()) / disp)
+        assert float(d.pow(2).mean().sqrt()) <= 0.05 * disp, (k, float(d.pow(2).mean().sqrt()) / disp)
+    print(f"bf16 iteration {name}: worst per-tensor RMS weight deviation = {worst:.4f} of the 40-step displacement")
+
+
+def test_update_graph_is_dropped_when_a_workspace_moves():
+    """ops.scratch() re-allocates a workspace when a larger one is requested; a captured update graph would then
+    replay into freed memory.  The runner notices (scratch generation) and falls back to eager + re-capture; results stay
+    bit-identical to a run that never used a graph."""
+    from partmanip_b200 import ops
+    from partmanip_b200.algorithms import ppo
+    from partmanip_b200.envs import FakeVecEnv
+    from tests.helpers import PN, ppo_cfg
+    outs = []
+    for disturb in (False, True):
+        torch.manual_seed(4)
+        env = FakeVecEnv(16, 3072, 10, DEV, cloud=True, seed=8)
+        r = ppo(env, ppo_cfg(16, PN, device=DEV, cuda_graph=True), _Logger())
+        curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+        gen = torch.Generator().manual_seed(0)
+        for it in range(4):
+            eps = torch.randn(8, 16, 10, generator=gen).to(DEV)
+            last_obs, last_values = r.collect(curr, None, eps=eps)
+            r.storage.compute_returns(last_values, r.gamma, r.lam)
+            if disturb and it == 2:
+                assert r._graph is not None
+                ops.scratch(ops._scratch[(DEV, "adam")].numel() + 4096, DEV, "adam")   # somebody else grows a workspace the graph uses
+            r.update(it + 1)
+            if disturb and it == 2:
+                assert r._graph is None                                        # dropped, this update ran eagerly
+            r.storage.clear()
+            curr = r._ingest(last_obs.clone(), r.storage.obs_slot())
+        outs.append({k: v.clone() for k, v in r.actor_critic.state_dict().items()})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
 
 
 def test_checkpoint_roundtrip_and_reference_format(tmp_path):
@@ -248,6 +326,7 @@ def test_checkpoint_roundtrip_and_reference_format(tmp_path):
     assert torch.equal(r.optimizer_actor.exp_avg, r2.optimizer_actor.exp_avg)
     assert r2.optimizer_critic.step_count == r.optimizer_critic.step_count and r2.curr_iter == 7
     assert torch.equal(r.state_norm.running_ms.mean, r2.state_norm.running_ms.mean)
+    assert r2.actor_critic.rng_state() == r.actor_critic.rng_state() and "b200_rng" in ck
 
 
 def test_storage_overflow_and_sampler_geometry():

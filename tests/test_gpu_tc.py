@@ -15,6 +15,26 @@ def cu(t):
     return t.to(DEV).contiguous()
 
 
+def _oracle_grads_given_argmax(w, x, am, act, point_num=1024, proprio=0):
+    """Reference gradients of sum(y^2) with the max-pool routed to the KERNEL's winning points (`am`, (B,512)).  Two points
+    whose layer-3 values differ by less than the bf16 forward's error may swap places in the argmax; with the routing fixed
+    the remaining difference is operand rounding only, so the gate can be tight.  x: already-centred input rows."""
+    import torch.nn.functional as F
+    wl = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    b = x.shape[0]
+    pc = (x[:, :-proprio] if proprio else x).reshape(b, point_num, -1)
+    h = O.pointnet_encode(wl, pc, act)
+    feat = h.gather(1, am.long()[:, None, :]).squeeze(1)
+    if proprio:
+        feat = torch.cat((feat, x[:, -proprio:]), dim=-1)
+    f = O.activation(act)
+    o = f(F.linear(feat, wl["final_mlp.0.weight"], wl["final_mlp.0.bias"]))
+    o = f(F.linear(o, wl["final_mlp.2.weight"], wl["final_mlp.2.bias"]))
+    y = F.linear(o, wl["final_mlp.4.weight"], wl["final_mlp.4.bias"])
+    y.square().sum().backward()
+    return y.detach(), {k: v.grad for k, v in wl.items()}
+
+
 def _has_tc():
     from partmanip_b200._lib import lib
     return bool(lib.pm_has_tcgen05())
@@ -61,12 +81,16 @@ def test_tc_pointnet_golden_outputs_and_training_step():
     y = net(cu(g["x"]))
     assert close(y.detach().cpu(), g["y"], 1e-2, 1e-2), max_err(y.detach().cpu(), g["y"])
     y.square().sum().backward()
-    # gradients flow through the fp32 critical-point backward; with a bf16 forward they agree with the reference's
-    # to the forward's accuracy except on rows whose argmax flipped between near-tied points
+    # Gradients through the tcgen05 backward.  (a) against the reference recording itself: every tensor within 5 % relative L2
+    # (the residue is rows whose argmax flipped between near-tied points — measured in round 1: <= 3 %); (b) with the max-pool
+    # routed to the kernel's own winners the flip freedom is gone and what remains is bf16 operand rounding: 2 % gate.
+    am = net.runner._bufs[g["x"].shape[0]]["argmax"].cpu()
+    _, forced = _oracle_grads_given_argmax(sub(g, "w"), g["x"], am, "tanh")
     for k, v in sub(g, "g").items():
         got = dict(net.named_parameters())[k].grad.cpu()
         rel = float((got - v).norm() / (v.norm() + 1e-12))
-        assert rel < 0.1, (k, rel)
+        rel_f = float((got - forced[k]).norm() / (forced[k].norm() + 1e-12))
+        assert rel < 5e-2 and rel_f < 2e-2, (k, rel, rel_f)
 
 
 @pytest.mark.parametrize("B,N,C,act", [(1, 1024, 3, "tanh"), (8, 1024, 3, "tanh"), (75, 1024, 3, "tanh"), (301, 256, 3, "tanh"),
@@ -118,9 +142,36 @@ def test_tc_pointnet_submean_proprio_golden_bf16():
     assert close(y.detach().cpu(), g["y"], 1e-2, 1e-2), max_err(y.detach().cpu(), g["y"])
     assert close(x.cpu(), g["x_after"], 1e-5, 1e-6)
     y.square().sum().backward()
+    am = net.runner._bufs[g["x"].shape[0]]["argmax"].cpu()
+    _, forced = _oracle_grads_given_argmax(sub(g, "w"), g["x_after"], am, "tanh", proprio=p)
     for k, v in sub(g, "g").items():
         got = dict(net.named_parameters())[k].grad.cpu()
-        assert bool(torch.isfinite(got).all()) and float((got - v).norm() / (v.norm() + 1e-12)) < 0.15, k
+        rel = float((got - v).norm() / (v.norm() + 1e-12))
+        rel_f = float((got - forced[k]).norm() / (forced[k].norm() + 1e-12))
+        assert bool(torch.isfinite(got).all()) and rel < 5e-2 and rel_f < 2e-2, (k, rel, rel_f)
+
+
+def test_tc_pointnet_critic_head_golden_bf16():
+    """The critic (one output, network.py:152-159 with output_dim=1) in bf16 mode against a recording of the unmodified reference
+    class (tests/golden/pointnet_critic_out1.npz): value within the 1e-2 gate, gradients as above."""
+    if not _has_tc():
+        pytest.skip("library built without the tcgen05 encoder")
+    from partmanip_b200.algorithms.algo_utils.network import PointNet
+    g = load_golden("pointnet_critic_out1.npz")
+    net = PointNet(3072, 1, dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, precision="bf16"), 0)
+    net.load_state_dict(sub(g, "w"))
+    net.to(DEV)
+    y = net(cu(g["x"]))
+    assert tuple(y.shape) == (g["x"].shape[0], 1)
+    assert close(y.detach().cpu(), g["y"], 1e-2, 1e-2), max_err(y.detach().cpu(), g["y"])
+    y.square().sum().backward()
+    am = net.runner._bufs[g["x"].shape[0]]["argmax"].cpu()
+    _, forced = _oracle_grads_given_argmax(sub(g, "w"), g["x"], am, "tanh")
+    for k, v in sub(g, "g").items():
+        got = dict(net.named_parameters())[k].grad.cpu()
+        rel = float((got - v).norm() / (v.norm() + 1e-12))
+        rel_f = float((got - forced[k]).norm() / (forced[k].norm() + 1e-12))
+        assert rel < 5e-2 and rel_f < 2e-2, (k, rel, rel_f)
 
 
 def test_tc_unsupported_shapes_fail_loudly():

@@ -123,7 +123,6 @@ def test_tsdfvolume_sparse_voxel_end_to_end():
     assert np.array_equal(out, T.sparse_voxel(fused, 40))
 
 
-@pytest.mark.skipif(os.environ.get("PM_RUN_UNVERIFIED") != "1", reason="experimental kernel written after the round's GPU budget was spent")
 def test_onepass_integrate_is_bit_identical_to_the_two_pass_kernel():
     from partmanip_b200 import ops
     E, M, H, W = G["depth"].shape
@@ -134,3 +133,42 @@ def test_onepass_integrate_is_bit_identical_to_the_two_pass_kernel():
     a = ops.tsdf_integrate(d, pix_off, pix_z, float(G["size"]), R)
     b = ops.tsdf_integrate(d, pix_off, pix_z, float(G["size"]), R, onepass=True)
     assert torch.equal(a, b)
+    assert float(np.abs(b.cpu().numpy() - G["tsdf"]).max()) <= 1e-6            # and it reproduces the reference recording
+
+
+def test_config5_standin_sparse_voxels_into_pointnet_bf16():
+    """BASELINE config 5's stand-in (the reference has no Sparse-UNet; its `depth_sparse` observation feeds PointNet as
+    1024 x 4): depth images -> TSDF fusion -> 1024 farthest band voxels (x, y, z, tsdf) (utils/depth2tsdf.py:88-120) -> PointNet
+    with C = 4 on the tcgen05 path (network.py:141-198), end to end against the oracle chain at the bf16 gate; the observation
+    itself (integer coordinates + gathered values) must be exact."""
+    from oracle import ppo_oracle as O
+    from partmanip_b200.algorithms.algo_utils.network import PointNet
+    from partmanip_b200.utils.depth2tsdf import TSDFVolume
+    from tests.helpers import close, max_err
+    E, M, H, W, R = 6, 3, 72, 128, 50
+    rng = np.random.default_rng(77)
+    fx = W / 2.0 / np.tan(np.deg2rad(69.75) / 2.0)
+    intr = np.array([[fx, 0, W // 2], [0, fx, H // 2], [0, 0, 1]])
+    poses, org = G["cam_pose"][:M], [-0.25, -0.25, -0.0503]
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    depth = np.stack([np.stack([0.62 + 0.08 * np.sin(0.05 * xx + e) * np.cos(0.07 * yy + m) for m in range(M)]) for e in range(E)])
+    depth = (depth + 0.002 * rng.standard_normal(depth.shape)).astype(np.float32)
+    vol = TSDFVolume(DEV, size=0.5, resolution=R, _vol_origin=org)
+    vol.register_camera(poses, intr, H, W, E)
+    obs = vol.sparse_voxel(torch.from_numpy(depth).to(DEV))
+    assert tuple(obs.shape) == (E, 1024, 4)
+    fused = vol.integrate(torch.from_numpy(depth).to(DEV)).cpu().numpy()
+    want_obs = T.sparse_voxel(fused, 1024)
+    assert np.array_equal(obs.cpu().numpy(), want_obs)
+    torch.manual_seed(5)
+    net = PointNet(4096, 10, dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, precision="bf16"), 0)
+    assert net.in_channels == 4
+    w = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net.to(DEV)
+    # the voxel coordinates are 0..49: scale into the unit box like a `depth_sparse` consumer would before the first Linear
+    scale = torch.tensor([1 / R, 1 / R, 1 / R, 1.0], device=DEV)
+    x = (obs * scale).reshape(E, 4096).contiguous()
+    with torch.no_grad():
+        y = net(x)
+    want = O.pointnet_forward(w, (torch.from_numpy(want_obs) * scale.cpu()).reshape(E, 4096))
+    assert close(y.cpu(), want, 1e-2, 1e-2), max_err(y.cpu(), want)

@@ -77,7 +77,7 @@ def _runner(monkeypatch, **over):
     r.teacher = _Student()
     r.stu_obs_mode, r.tea_obs_mode = 'pc', 'state'
     r.n_steps, r.max_iter, r.curr_iter, r.eval_freq, r.save_freq, r.eval_round = 3, 4, 0, 2, 100, 2
-    r.max_episode_length, r.test_only, r.save_video, r.reward_reset = 5, False, False, False
+    r.max_episode_length, r.test_only, r.save_video, r.save_pose, r.reward_reset = 5, False, False, False, False
     r.total_envsteps = r.total_time = 0
     r.update = lambda it: r.log_dict.update({'Train/learning_rate': 0.1, 'Train/dagger_loss': 1.0 / it})
     for k, v in over.items():
@@ -126,3 +126,48 @@ def test_reward_reset_rule(monkeypatch):
     r.run()
     prog = r.vec_env.progress_buf
     assert int(prog[0]) == 15 and r.vec_env.dagger_reward_reset.shape == (4,) and r.vec_env.dagger_reward_reset.dtype == torch.bool
+
+
+def test_dagger_optimizer_state_dict_is_the_reference_adams():
+    """dagger.py:56 builds Adam(student.parameters()): parameter order [log_std, actor.*, critic.*], only the actor tensors ever
+    get a gradient (torch's Adam keeps no state for the others).  The flat optimiser must read and write exactly that dict:
+    actor moments at indices 1..n, one param group over ALL tensors — checked against a real torch.optim.Adam in both
+    directions (a reference checkpoint resumes here; a checkpoint written here resumes in the reference)."""
+    import torch.nn as nn
+    from partmanip_b200.algorithms.algo_utils import ActorCritic
+    torch.manual_seed(0)
+    model_cfg = dict(action_std=0.5, action_activate="tanh", clipAction=1.0, network=dict(name="MLP", hid_dim=[16, 8], activation="tanh"))
+    r = D.dagger.__new__(D.dagger)
+    r.stu_input_obs, r.num_actions, r.model_cfg, r.device, r.lr = 6, 3, model_cfg, "cpu", 1e-3
+    r._build_student(0)
+    names = [k for k, _ in r.student.named_parameters()]
+    assert names[0] == "log_std" and names[1].startswith("actor.") and names[-1].startswith("critic.")
+    n_actor = sum(k.startswith("actor.") for k in names)
+    # the reference side: a plain module with identical parameter order, two Adam steps on actor gradients only
+    twin = ActorCritic(6, 3, model_cfg)
+    twin.load_state_dict(r.student.state_dict())
+    ref_opt = torch.optim.Adam(twin.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(2):
+        for k, p in twin.named_parameters():
+            p.grad = torch.randn(p.shape, generator=g) if k.startswith("actor.") else None
+        ref_opt.step()
+    ref_sd = ref_opt.state_dict()
+    assert sorted(ref_sd["state"]) == list(range(1, 1 + n_actor)) and ref_sd["param_groups"][0]["params"] == list(range(len(names)))
+    # reference checkpoint -> here
+    r.optimizer.load_state_dict(ref_sd)
+    assert r.optimizer.step_count == 2
+    for (k, p), m in zip([kp for kp in twin.named_parameters() if kp[0].startswith("actor.")], r.optimizer._views(r.optimizer.exp_avg)):
+        assert torch.equal(m, ref_sd["state"][names.index(k)]["exp_avg"]), k
+    # here -> the reference's Adam accepts it and holds the same moments
+    ours = r.optimizer.state_dict()
+    assert sorted(ours["state"]) == sorted(ref_sd["state"]) and ours["param_groups"][0]["params"] == list(range(len(names)))
+    ref2 = torch.optim.Adam(ActorCritic(6, 3, model_cfg).parameters(), lr=1.0)
+    ref2.load_state_dict(ours)
+    for i in ours["state"]:
+        assert torch.equal(ref2.state_dict()["state"][i]["exp_avg_sq"], ref_sd["state"][i]["exp_avg_sq"])
+    # a dict with another layout (e.g. written for the actor alone) is refused instead of being misassigned
+    import pytest
+    bad = {"state": {}, "param_groups": [{"lr": 1e-3, "params": list(range(n_actor))}]}
+    with pytest.raises(ValueError, match="covers"):
+        r.optimizer.load_state_dict(bad)

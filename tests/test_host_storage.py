@@ -77,3 +77,18 @@ def test_dagger_ring_cursors(monkeypatch):
         st.add_transitions_dagger(torch.full((4, 6), float(i)), torch.full((4, 5), float(10 + i)))
     assert st.cur_buf_size == 12 and st.mix_buf_ind == 4                               # wrapped: step 3 overwrote rows 0..3
     assert float(st.observations[0, 0]) == 3.0 and float(st.observations[4, 0]) == 1.0 and float(st.tea_obs[0, 0]) == 13.0
+
+
+def test_random_sampler_reproduces_the_reference_permutation():
+    """storage.py:133-137: BatchSampler(SubsetRandomSampler(range(n)), size, drop_last=True) draws torch.randperm(n) from the host
+    default generator; for the same torch.manual_seed ours yields the same index batches (two epochs = two fresh permutations)."""
+    from torch.utils.data.sampler import BatchSampler, SubsetRandomSampler
+    st = S.RolloutStorage.__new__(S.RolloutStorage)
+    st.sampler, st.device, st.cur_buf_size = "random", "cpu", 8 * 37
+    torch.manual_seed(123)
+    ref = BatchSampler(SubsetRandomSampler(range(st.cur_buf_size)), min(st.cur_buf_size // 8, 2048), drop_last=True)
+    want = [list(b) for _ in range(2) for b in ref]
+    torch.manual_seed(123)
+    ours = st.mini_batch_generator(8)
+    got = [b.tolist() for _ in range(2) for b in ours]
+    assert got == want
