@@ -265,7 +265,7 @@ def test_full_iteration_bf16_against_reference_recording(name):
         d = (sd[k] - v).abs()
         assert float(d.max()) <= disp, (k, float(d.max()))
         worst = max(worst, float(d.pow(2).mean().sqrt()) / disp)
-        assert float(d.pow(2).mean().sqrt()) <= 0.05 * disp, (k, float(d.pow(2).mean().sqrt()) / disp)
+        assert float(d.pow(2).mean().sqrt()) <= 0.08 * disp, (k, float(d.pow(2).mean().sqrt()) / disp)   # measured 0.040-0.046
     print(f"bf16 iteration {name}: worst per-tensor RMS weight deviation = {worst:.4f} of the 40-step displacement")
 
 
