@@ -247,6 +247,21 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
 int pm_pointnet_bwd_tc_last_error(const void* ws, pm_stream_t s);
 
 /* ------------------------------------------------------------------------------------------
+ * K3t  the same dense layers on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM) — the state policy
+ * MLP 53 -> 512^3 -> 10 that `--algocfg ppo --taskcfg open_drawer` trains (cfg/algos/ppo.yaml:44-47, network.py:27-54),
+ * DAgger's teacher, and the dense layers of the fp32 critical-point encoder backward.  Tensors stay fp32 in HBM; tiles are
+ * converted on the fly.  precision: PM_PREC_BF16 = bf16 operands (1e-2 gate); PM_PREC_FP32 = every value split into three
+ * bf16 terms (24 mantissa bits, fp32 exponent range) and six term-pair MMAs per product (1e-4 gate).  Same argument
+ * meaning as pm_linear_forward / pm_linear_backward.
+ * ------------------------------------------------------------------------------------------ */
+int pm_linear_forward_tc(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int M, int N, int K,
+                         int act, int precision, const int32_t* m_dev, pm_stream_t s);
+size_t pm_linear_backward_tc_ws_bytes(int M, int N, int K);
+int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const float* dpre, int64_t lddpre, float* dW, float* db,
+                          float* dx, int64_t lddx, int M, int N, int K, int act_prev, int precision, const int32_t* m_dev,
+                          void* ws, pm_stream_t s);
+
+/* ------------------------------------------------------------------------------------------
  * K7  grad-norm clip + Adam on flat buffers
  * replaces nn.utils.clip_grad_norm_ + torch.optim.Adam.step (ppo.py:351-353, 381-382).
  * The flat buffer is [clipped params (n_clip) | unclipped tail (log_std, Q8)].

@@ -53,6 +53,9 @@ SIGNATURES = {
     "pm_linear_forward": (I, [P, L, P, P, P, L, I, I, I, I, P, P]),
     "pm_linear_backward_ws_bytes": (SZ, [I, I, I]),
     "pm_linear_backward": (I, [P, L, P, P, L, P, P, P, L, I, I, I, I, P, P, P]),
+    "pm_linear_forward_tc": (I, [P, L, P, P, P, L, I, I, I, I, I, P, P]),
+    "pm_linear_backward_tc_ws_bytes": (SZ, [I, I, I]),
+    "pm_linear_backward_tc": (I, [P, L, P, P, L, P, P, P, L, I, I, I, I, I, P, P, P]),
     "pm_pointnet_head_forward": (I, [P, L, I, I, EP, I, I, I, P, P, P, L, P]),
     "pm_pointnet_head_backward_ws_bytes": (SZ, [I, I]),
     "pm_pointnet_head_backward": (I, [P, L, I, I, EP, I, I, I, P, P, P, L, EP, P, L, I, P, SZ, P]),
@@ -108,7 +111,7 @@ KERNELS_PER_CALL = {
     "pm_rms_colsum": 2, "pm_rms_colsqdev": 2, "pm_rms_update": 1, "pm_rms_normalize": 1, "pm_rms_forward": 6, "pm_gae": 1,
     "pm_normalize": 1, "pm_normalize_inplace": 1, "pm_randn": 1, "pm_policy_sample": 1, "pm_action_activation": 1,
     "pm_policy_logprob": 1, "pm_ppo_actor_loss": 2, "pm_ppo_actor_finalize": 1, "pm_value_loss": 2, "pm_abs_sum": 2,
-    "pm_accumulate": 1, "pm_dagger_loss": 2, "pm_linear_forward": 1, "pm_linear_backward": 4, "pm_pointnet_center": 1,
+    "pm_accumulate": 1, "pm_dagger_loss": 2, "pm_linear_forward": 1, "pm_linear_backward": 4, "pm_linear_forward_tc": 1, "pm_linear_backward_tc": 5, "pm_pointnet_center": 1,
     "pm_pointnet_encode_forward": 2, "pm_pointnet_encode_backward": 3, "pm_pointnet_head_forward": 1,
     "pm_pointnet_head_backward": 3, "pm_adam_step": 3, "pm_gather_rows": 1,
     "pm_copy_rows": 1,

@@ -69,7 +69,10 @@ class _MLPRunner(_Runner):
         L = len(net.linears)
         for i, lin in enumerate(net.linears):
             act = net.act_name if i != L - 1 else None
-            h = ops.linear_forward(h, lin.weight, lin.bias, act, out=buf["h"][i])
+            if net.precision == "fp32_ffma":
+                h = ops.linear_forward(h, lin.weight, lin.bias, act, out=buf["h"][i])
+            else:
+                h = ops.linear_forward_tc(h, lin.weight, lin.bias, act, net.precision, out=buf["h"][i])
         return h
 
     def backward(self, x: torch.Tensor, dout: torch.Tensor, grads: List[torch.Tensor]):
@@ -83,13 +86,20 @@ class _MLPRunner(_Runner):
             lin = net.linears[i]
             inp = x if i == 0 else buf["h"][i - 1]
             dx = None if i == 0 else buf["d"][i - 1]
-            ops.linear_backward(inp, lin.weight, dpre, grads[2 * i], grads[2 * i + 1], dx,
-                                net.act_name if i > 0 else None)
+            if net.precision == "fp32_ffma":
+                ops.linear_backward(inp, lin.weight, dpre, grads[2 * i], grads[2 * i + 1], dx, net.act_name if i > 0 else None)
+            else:
+                ops.linear_backward_tc(inp, lin.weight, dpre, grads[2 * i], grads[2 * i + 1], dx,
+                                       net.act_name if i > 0 else None, net.precision)
             dpre = dx
 
 
 class MLP(nn.Module):
-    """network.py:27-54.  Linear(in,h0)-act-...-Linear(h_last,out); orthogonal init, gains sqrt2.. then 1 / 0.01."""
+    """network.py:27-54.  Linear(in,h0)-act-...-Linear(h_last,out); orthogonal init, gains sqrt2.. then 1 / 0.01.
+
+    Build extension: `net_cfg['precision']` selects the arithmetic of the dense layers — "fp32" (default): tcgen05 with every
+    fp32 value split into three bf16 terms, 1e-4 parity gate; "bf16": tcgen05 with bf16 operands, 1e-2 gate; "fp32_ffma": the
+    CUDA-core kernels of dense.cu."""
 
     def __init__(self, input_dim, output_dim, net_cfg, proprio_shape=0):
         super().__init__()
@@ -110,6 +120,9 @@ class MLP(nn.Module):
             torch.nn.init.orthogonal_(module.weight, gain=init_weights[idx])
         self.act_name = net_cfg['activation']
         self.dims = [input_dim, *hidden_dim, output_dim]
+        self.precision = net_cfg.get('precision', 'fp32')
+        if self.precision not in ("fp32", "bf16", "fp32_ffma"):
+            raise NotImplementedError(f"precision {self.precision!r}")
         self.runner = _MLPRunner(self)
 
     @property

@@ -282,6 +282,33 @@ def linear_backward(x: Tensor, W: Tensor, dpre: Tensor, dW: Tensor, db: Optional
                                  PM_ACT[act_prev], _p(m_dev), _p(ws), _stream()), "pm_linear_backward")
 
 
+def linear_forward_tc(x: Tensor, W: Tensor, b: Optional[Tensor], act, precision: str, out: Optional[Tensor] = None,
+                      m_dev: Optional[Tensor] = None) -> Tensor:
+    """nn.Linear (+ activation) on tcgen05: precision "bf16" (1e-2 gate) or "fp32" (three-term bf16 split, 1e-4 gate)."""
+    M, K, ldx = _rows(_f32(x, "x"), "x")
+    N = W.shape[0]
+    assert W.shape[1] == K and W.is_contiguous() and _f32(W, "W") is W
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    _, _, ldy = _rows(out, "out")
+    check(lib.pm_linear_forward_tc(_p(x), ldx, _p(W), _p(b), _p(out), ldy, M, N, K, PM_ACT[act], PM_PREC[precision], _p(m_dev),
+                                   _stream()), "pm_linear_forward_tc")
+    return out
+
+
+def linear_backward_tc(x: Tensor, W: Tensor, dpre: Tensor, dW: Tensor, db: Optional[Tensor], dx: Optional[Tensor], act_prev,
+                       precision: str, m_dev: Optional[Tensor] = None):
+    M, K, ldx = _rows(_f32(x, "x"), "x")
+    N = W.shape[0]
+    _, _, ldd = _rows(_f32(dpre, "dpre"), "dpre")
+    lddx = 0
+    if dx is not None:
+        _, _, lddx = _rows(_f32(dx, "dx"), "dx")
+    ws = scratch(lib.pm_linear_backward_tc_ws_bytes(M, N, K), x.device, "linbwd_tc")
+    check(lib.pm_linear_backward_tc(_p(x), ldx, _p(W), _p(dpre), ldd, _p(dW), _p(db), _p(dx), lddx, M, N, K, PM_ACT[act_prev],
+                                    PM_PREC[precision], _p(m_dev), _p(ws), _stream()), "pm_linear_backward_tc")
+
+
 # ------------------------------------------------------------------------------------------- K3b fused head
 def pointnet_head_forward(feat: Tensor, head_params: Sequence[Tensor], out_dim: int, act, h1: Tensor, h2: Tensor,
                           out: Tensor, precision: str = "fp32") -> Tensor:
