@@ -48,8 +48,11 @@ typedef enum {
 
 /* arithmetic mode of the encoder's two GEMM layers */
 typedef enum {
-  PM_PREC_FP32 = 0, /* FFMA, fp32 everywhere: parity gate 1e-4 */
-  PM_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 accumulate in TMEM: parity gate 1e-2 */
+  PM_PREC_FP32 = 0,     /* the reference's precision (parity gate 1e-4) on the tensor cores: operands split into fp16 / bf16 terms,
+                           several tcgen05 MMAs per product, fp32 accumulate in TMEM; shapes the tcgen05 kernels do not take
+                           (N % 256 != 0, C > 4, max_mean pooling) run on the CUDA-core kernels */
+  PM_PREC_BF16 = 1,     /* tcgen05 bf16 operands, fp32 accumulate in TMEM: parity gate 1e-2 */
+  PM_PREC_FP32_FFMA = 2 /* fp32 on CUDA cores only (FFMA): parity gate 1e-4 */
 } pm_precision;
 
 const char* pm_last_error(void);
@@ -229,6 +232,8 @@ size_t pm_pointnet_encode_forward_ws_bytes(int B, int N, int C, int precision);
 /* diagnostic for PM_PREC_BF16: the device-side protocol error word the last launch left in `ws`
  * (0 = clean; 1xx = a bounded mbarrier wait expired).  Synchronises the stream. */
 int pm_pointnet_tc_last_error(const void* ws, pm_stream_t s);
+/* the same diagnostic for a PM_PREC_FP32 launch that ran on the split-fp16 tcgen05 kernel */
+int pm_pointnet_tc3_last_error(const void* ws, pm_stream_t s);
 
 /* Backward through max-pool + per-point MLP.  The max-pool routes dfeat[b,c] to the single point
  * argmax[b,c], so only the unique "critical" points of each cloud carry gradient: their

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pm_pointnet_encode_forward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, P, SZ, P]),
     "pm_pointnet_encode_forward_ws_bytes": (SZ, [I, I, I, I]),
     "pm_pointnet_tc_last_error": (I, [P, P]),
+    "pm_pointnet_tc3_last_error": (I, [P, P]),
     "pm_pointnet_encode_backward_ws_bytes": (SZ, [I, I, I, I, I]),
     "pm_pointnet_encode_backward": (I, [P, L, I, I, I, EP, I, I, P, P, L, P, P, EP, P, SZ, P]),
     "pm_pointnet_bwd_tc_last_error": (I, [P, P]),
@@ -83,7 +84,7 @@ SIGNATURES = {
 }
 
 PM_ACT = {None: 0, "none": 0, "tanh": 1, "relu": 2, "crelu": 2, "elu": 3, "selu": 4, "lrelu": 5, "sigmoid": 6}
-PM_PREC = {"fp32": 0, "bf16": 1}
+PM_PREC = {"fp32": 0, "bf16": 1, "fp32_ffma": 2}
 
 
 class PMError(RuntimeError):

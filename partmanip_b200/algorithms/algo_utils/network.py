@@ -231,7 +231,7 @@ class PointNet(nn.Module):
         self.act_name = net_cfg['activation']
         self.output_dim = output_dim
         self.precision = net_cfg.get('precision', 'fp32')
-        if self.precision not in ("fp32", "bf16"):
+        if self.precision not in ("fp32", "bf16", "fp32_ffma"):
             raise NotImplementedError(f"precision {self.precision!r}")
         # the head (0.04 % of the FLOPs) stays on the fp32 FFMA kernels by default: its tcgen05 variant (head_tc.cu,
         # `head_precision: bf16`) measured no faster at B = 2048 (16-32 CTAs, staging-latency bound) and costs accuracy

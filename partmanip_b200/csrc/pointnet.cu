@@ -19,6 +19,18 @@ extern "C" int pm_pointnet_encode_backward_tc(const float* x, int64_t ldx, int B
                                               const pm_encoder_grads* g, void* ws, size_t ws_bytes, pm_stream_t s);
 extern "C" size_t pm_pointnet_encode_backward_tc_ws_bytes(int B, int N, int C);
 
+extern "C" int pm_linear_forward_tc(const float* x, int64_t ldx, const float* W, const float* b, float* y, int64_t ldy, int M, int N,
+                                    int K, int act, int precision, const int32_t* m_dev, pm_stream_t s);
+extern "C" size_t pm_linear_backward_tc_ws_bytes(int M, int N, int K);
+extern "C" int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const float* dpre, int64_t lddpre, float* dW,
+                                     float* db, float* dx, int64_t lddx, int M, int N, int K, int act_prev, int precision,
+                                     const int32_t* m_dev, void* ws, pm_stream_t s);
+
+extern "C" int pm_pointnet_encode_forward_tc3(const float* x, int64_t ldx, int B, int N, int C, const pm_encoder_params* p, int act,
+                                              float* feat, int64_t ldf, int32_t* argmax, void* ws, size_t ws_bytes, pm_stream_t s);
+extern "C" size_t pm_pointnet_encode_forward_tc3_ws_bytes(int B, int N, int C);
+extern "C" int pm_pointnet_encode_forward_tc3_supported(int N, int C);
+
 namespace {
 
 constexpr int TP = 64;          // points per tile
@@ -468,9 +480,12 @@ inline BwdWs carve_bwd(void* ws, int B, int N, int C, int with_mean) {
   w.dw3part = (float*)take((size_t)w.slabs * 512 * 256 * 4);
   w.db3part = (float*)take((size_t)w.slabs * 512 * 4);
   w.gm = (float*)take(with_mean ? (size_t)B * 256 * 4 : 0);
-  size_t l1 = pm_linear_backward_ws_bytes((int)(rmax > INT32_MAX ? INT32_MAX : rmax), 256, 128);
-  size_t l2 = pm_linear_backward_ws_bytes((int)(rmax > INT32_MAX ? INT32_MAX : rmax), 128, C);
+  const int rm = (int)(rmax > INT32_MAX ? INT32_MAX : rmax);
+  size_t l1 = pm_linear_backward_ws_bytes(rm, 256, 128);
+  size_t l2 = pm_linear_backward_ws_bytes(rm, 128, C);
+  size_t l3 = pm_linear_backward_tc_ws_bytes(rm, 256, 128);
   w.lin_bytes = l1 > l2 ? l1 : l2;
+  if (l3 > w.lin_bytes) w.lin_bytes = l3;
   w.lin = (float*)take(w.lin_bytes);
   w.total = off;
   return w;
@@ -489,6 +504,7 @@ int pm_pointnet_center(float* x, int64_t ldx, int B, int N, int C, pm_stream_t s
 
 size_t pm_pointnet_encode_forward_ws_bytes(int B, int N, int C, int precision) {
   if (precision == PM_PREC_BF16) return pm_pointnet_encode_forward_tc_ws_bytes(B, N, C);
+  if (precision == PM_PREC_FP32 && pm_pointnet_encode_forward_tc3_supported(N, C)) return pm_pointnet_encode_forward_tc3_ws_bytes(B, N, C);
   return 0;
 }
 
@@ -504,7 +520,10 @@ int pm_pointnet_encode_forward(const float* x, int64_t ldx, int B, int N, int C,
     PM_REQUIRE(!feat_mean && !h2mean, PM_ERR_UNSUPPORTED, "bf16 encoder: max_mean pooling runs in PM_PREC_FP32 only");
     return pm_pointnet_encode_forward_tc(x, ldx, B, N, C, p, act, feat, ldf, argmax, ws, ws_bytes, s);
   }
-  PM_REQUIRE(precision == PM_PREC_FP32, PM_ERR_ARG, "pm_pointnet_encode_forward: precision %d", precision);
+  PM_REQUIRE(precision == PM_PREC_FP32 || precision == PM_PREC_FP32_FFMA, PM_ERR_ARG, "pm_pointnet_encode_forward: precision %d", precision);
+  // fp32 parity mode: the split-fp16 tcgen05 kernel where it applies (max pooling only, N % 256 == 0, C <= 4), else CUDA cores
+  if (precision == PM_PREC_FP32 && !feat_mean && !h2mean && pm_pointnet_encode_forward_tc3_supported(N, C))
+    return pm_pointnet_encode_forward_tc3(x, ldx, B, N, C, p, act, feat, ldf, argmax, ws, ws_bytes, s);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(encoder_fwd_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
@@ -532,7 +551,8 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
     PM_REQUIRE(!dfeat_mean, PM_ERR_UNSUPPORTED, "bf16 encoder backward: max_mean pooling runs in PM_PREC_FP32 only");
     return pm_pointnet_encode_backward_tc(x, ldx, B, N, C, p, act, dfeat, lddf, argmax, g, ws, ws_bytes, s);
   }
-  PM_REQUIRE(precision == PM_PREC_FP32, PM_ERR_ARG, "pm_pointnet_encode_backward: precision %d", precision);
+  PM_REQUIRE(precision == PM_PREC_FP32 || precision == PM_PREC_FP32_FFMA, PM_ERR_ARG, "pm_pointnet_encode_backward: precision %d", precision);
+  const bool tc = precision == PM_PREC_FP32;     // the two 128<->256 layers on tcgen05 (three-term bf16 split, 1e-4 gate)
   PM_REQUIRE(!dfeat_mean || h2mean, PM_ERR_ARG, "pm_pointnet_encode_backward: the mean-pool branch needs h2mean from the forward");
   const int with_mean = dfeat_mean != nullptr;
   BwdWs w = carve_bwd(ws, B, N, C, with_mean);
@@ -549,7 +569,9 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
   // 2. recompute their activations
   const int grid_rows = 8 * PM_NUM_SMS;
   crit_layer1_kernel<<<grid_rows, 128, 0, st>>>(w.Xc, C, p->W1, p->b1, act, w.r_dev, w.H1c);
-  if ((rc = pm_linear_forward(w.H1c, 128, p->W2, p->b2, w.H2c, 256, rmax, 256, 128, act, w.r_dev, s))) return rc;
+  if (tc) rc = pm_linear_forward_tc(w.H1c, 128, p->W2, p->b2, w.H2c, 256, rmax, 256, 128, act, PM_PREC_FP32, w.r_dev, s);
+  else rc = pm_linear_forward(w.H1c, 128, p->W2, p->b2, w.H2c, 256, rmax, 256, 128, act, w.r_dev, s);
+  if (rc) return rc;
   // 3. layer 3: dPre2 rows and dW3/db3
   if (with_mean) mean_gm_kernel<<<B, 256, 0, st>>>(dfeat_mean, lddf, p->W3, 1.f / (float)N, w.gm);
   crit_dh2_kernel<<<grid_rows, 256, 0, st>>>(dfeat, lddf, p->W3, w.H2c, w.row_b, w.row_cbeg, w.row_ccnt, w.chan_sorted,
@@ -561,8 +583,10 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
   if (with_mean) mean_dw3_kernel<<<512 / DW3_CH, 256, 0, st>>>(dfeat_mean, lddf, h2mean, B, g->W3, g->b3);
   PM_CHECK_LAUNCH("pm_pointnet_encode_backward/crit");
   // 4. layer 2: dW2, db2, dPre1 = (dPre2 W2) * act'(H1c)
-  if ((rc = pm_linear_backward(w.H1c, 128, p->W2, w.dPre2, 256, g->W2, g->b2, w.dPre1, 128, rmax, 256, 128, act,
-                               w.r_dev, w.lin, s))) return rc;
+  if (tc) rc = pm_linear_backward_tc(w.H1c, 128, p->W2, w.dPre2, 256, g->W2, g->b2, w.dPre1, 128, rmax, 256, 128, act, PM_PREC_FP32,
+                                     w.r_dev, w.lin, s);
+  else rc = pm_linear_backward(w.H1c, 128, p->W2, w.dPre2, 256, g->W2, g->b2, w.dPre1, 128, rmax, 256, 128, act, w.r_dev, w.lin, s);
+  if (rc) return rc;
   // 5. layer 1: dW1, db1 (no dx: the cloud is an input)
   if ((rc = pm_linear_backward(w.Xc, C, p->W1, w.dPre1, 128, g->W1, g->b1, nullptr, 0, rmax, 128, C, PM_ACT_NONE,
                                w.r_dev, w.lin, s))) return rc;

@@ -368,7 +368,7 @@ def pointnet_encode_forward(x: Tensor, N: int, C: int, enc_params: Sequence[Tens
         assert argmax.dtype == torch.int32 and argmax.is_contiguous() and argmax.shape == (B, 512)
     prec = PM_PREC[precision]
     nbytes = lib.pm_pointnet_encode_forward_ws_bytes(B, N, C, prec)
-    ws = scratch(nbytes, x.device, "encfwd") if nbytes else None
+    ws = scratch(nbytes, x.device, "encfwd" if prec == PM_PREC["bf16"] else "encfwd_fp32") if nbytes else None
     ps = _enc_struct(enc_params)
     check(lib.pm_pointnet_encode_forward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], prec,
                                          _p(feat), _p(feat_mean), ldf, _p(argmax), _p(h2mean), _p(ws), nbytes, _stream()),
@@ -393,6 +393,14 @@ def pointnet_tc_last_error(device) -> int:
     return int(lib.pm_pointnet_tc_last_error(_p(ws), _stream()))
 
 
+def pointnet_tc3_last_error(device) -> int:
+    """Protocol error word of the last fp32-mode (split-fp16 tcgen05) encoder launch on `device` (0 = clean).  Synchronises."""
+    ws = _scratch.get((str(device), "encfwd_fp32"))
+    if ws is None:
+        return 0
+    return int(lib.pm_pointnet_tc3_last_error(_p(ws), _stream()))
+
+
 def pointnet_bwd_tc_last_error(device) -> int:
     """Protocol error word of the last bf16 encoder-backward launch on `device` (0 = clean).  Synchronises."""
     ws = _scratch.get((str(device), "encbwd_bf16"))
@@ -410,7 +418,7 @@ def pointnet_encode_backward(x: Tensor, N: int, C: int, enc_params: Sequence[Ten
     assert fw == 512 and argmax.dtype == torch.int32 and argmax.is_contiguous()
     prec = PM_PREC[precision]
     nbytes = lib.pm_pointnet_encode_backward_ws_bytes(B, N, C, int(dfeat_mean is not None), prec)
-    ws = scratch(nbytes, x.device, "encbwd_bf16" if prec else "encbwd")
+    ws = scratch(nbytes, x.device, "encbwd_bf16" if prec == PM_PREC["bf16"] else "encbwd")
     ps, gs = _enc_struct(enc_params), _enc_struct(enc_grads)
     check(lib.pm_pointnet_encode_backward(_p(x), ldx, B, N, C, ct.byref(ps), PM_ACT[act], prec, _p(dfeat), _p(dfeat_mean), lddf,
                                           _p(argmax), _p(h2mean), ct.byref(gs), _p(ws), nbytes, _stream()),

@@ -30,12 +30,13 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-for prec in ("bf16", "fp32"):
-    if prec == "fp32" and len(sys.argv) > 1 and sys.argv[1] == "bf16":
+only = sys.argv[1].split(",") if len(sys.argv) > 1 else ("bf16", "fp32", "fp32_ffma")
+for prec in ("bf16", "fp32", "fp32_ffma"):
+    if prec not in only:
         continue
-    f = timeit(lambda i: ops.pointnet_encode_forward(xs[i % 8], N, C, enc, "tanh", prec, feat, None, am, None), 20 if prec == "bf16" else 3)
-    b = timeit(lambda i: ops.pointnet_encode_backward(xs[i % 8], N, C, enc, "tanh", dfeat, am, grads, precision=prec), 20 if prec == "bf16" else 3)
+    f = timeit(lambda i: ops.pointnet_encode_forward(xs[i % 8], N, C, enc, "tanh", prec, feat, None, am, None), 3 if prec == "fp32_ffma" else 20)
+    b = timeit(lambda i: ops.pointnet_encode_backward(xs[i % 8], N, C, enc, "tanh", dfeat, am, grads, precision=prec), 3 if prec == "fp32_ffma" else 20)
     fl = B * 2 * N * (C * 128 + 128 * 256 + 256 * 512)
     print(f"{prec}: forward {f:.3f} ms ({fl / f / 1e9:.0f} TFLOP/s)  backward {b:.3f} ms  uniq-crit/cloud "
           f"{float(torch.tensor([am[i].unique().numel() for i in range(16)]).float().mean()):.0f}")
-print("errs", ops.pointnet_tc_last_error(dev), ops.pointnet_bwd_tc_last_error(dev))
+print("errs", ops.pointnet_tc_last_error(dev), ops.pointnet_bwd_tc_last_error(dev), ops.pointnet_tc3_last_error(dev))

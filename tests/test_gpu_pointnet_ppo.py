@@ -35,13 +35,18 @@ def _build(name, precision="fp32"):
     return g, net.to(DEV)
 
 
+# "fp32" = the reference's precision on the tensor cores where the shape allows (split-fp16 tcgen05 forward, three-term bf16
+# tcgen05 GEMMs in the backward), "fp32_ffma" = CUDA cores only: both must hold the 1e-4 gate on every recording
+@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma"])
 @pytest.mark.parametrize("name", list(PN_CASES))
-def test_pointnet_golden_forward(name):
-    g, net = _build(name)
+def test_pointnet_golden_forward(name, precision):
+    from partmanip_b200 import ops
+    g, net = _build(name, precision)
     assert sum(p.numel() for p in net.parameters()) == int(g["n_params"])
     x = cu(g["x"])
     with torch.no_grad():
         y = net(x)
+    assert ops.pointnet_tc3_last_error(DEV) == 0
     assert close(y.cpu(), g["y"], 1e-4, 1e-5), max_err(y.cpu(), g["y"])
     # Q3: sub_mean centres the caller's tensor in place
     assert close(x.cpu(), g["x_after"], 1e-5, 1e-6)
@@ -49,9 +54,10 @@ def test_pointnet_golden_forward(name):
         assert not torch.equal(x.cpu(), g["x"])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp32_ffma"])
 @pytest.mark.parametrize("name", list(PN_CASES))
-def test_pointnet_golden_backward(name):
-    g, net = _build(name)
+def test_pointnet_golden_backward(name, precision):
+    g, net = _build(name, precision)
     y = net(cu(g["x"]))
     y.square().sum().backward()
     for k, v in sub(g, "g").items():
