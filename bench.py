@@ -5,9 +5,15 @@ One "step" = one full PPO iteration of the hot path with a zero-cost synthetic e
 T=8 x [state-norm -> random_act_cri -> add_transitions] + cri + compute_returns + update (5 epochs, actor phase then
 critic phase, 16 minibatches of 2048 at E=4096).  value = E*T*world / time per iteration.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E] [--precision bf16|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_gpu] [--envs E] [--precision bf16|fp32]
 
-Under torchrun (N>1) every rank owns E envs (weak scaling); gradients / KL sums / obs statistics are all-reduced.
+The headline line is the bf16 (tcgen05) mode.  At N=1 the same line also carries
+  modes.fp32      the same workload at the REFERENCE's precision (1e-4 gate; split-operand tcgen05 kernels),
+  gpu_baseline    the reference's path as eager PyTorch on the same GPU (fp32, TF32 off) — north_star's ">= 10x" denominator,
+  configs         BASELINE config 4 (DAgger, 2048 envs x 2048 pts, random sampler) and the shipped state-MLP PPO config,
+  cpu_baseline    the CPU oracle port on the host cores.
+Under torchrun (N>1) every rank owns E envs (weak scaling); gradients / KL sums / obs statistics are all-reduced, and the
+line carries `multi_gpu_parity` (replicas bit-identical across ranks, losses of N ranks x E envs vs ONE process with N*E envs).
 `--impl reference` times the reference's algorithm on the host cores (the CPU oracle port — the reference is
 Python/PyTorch and cannot be vendored) on a bounded sample of the same workload.
 Prints ONE JSON line on rank 0.
@@ -22,15 +28,19 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_OUT = sys.stdout
 
 T_STEPS, N_PTS, CH, ACT = 8, 1024, 3, 10
 F_POINTNET = 2 * N_PTS * (CH * 128 + 128 * 256 + 256 * 512) + 2 * (512 * 128 + 128 * 32 + 32 * ACT)   # 336.5 MFLOP
 ENC_FLOPS_PER_CLOUD = 2 * N_PTS * (CH * 128 + 128 * 256 + 256 * 512)
+# encoder backward, per (cloud, channel) ROW the kernel executes: recompute layer 2 (128x256), dH1 = dPre2.W2 (256x128),
+# dW2 += dPre2^T.H1 (256x128) as MMAs + the per-row dW3 / dPre2 epilogue (2 x 256 FMAs)
+BWD_FLOPS_PER_ROW = 2 * (3 * 128 * 256 + 2 * 256)
 
 
-def ppo_cfg(E, device, precision):
+def ppo_cfg(E, device, precision, net=None, **over):
     """Shipped cfg/algos/ppo.yaml hyper-parameters + the PointNet keys the reference's YAML lacks."""
-    return dict(
+    cfg = dict(
         num_envs=E, obs_mode="obs", succ_value=None, max_iterations=10 ** 9, n_steps=T_STEPS, n_updates=5,
         n_minibatches=8, device=device, eval_round=1, eval_frequence=10 ** 9, save_frequence=10 ** 9,
         test_only=False, save_pose=False, save_video=False, lr_schedule="fixed", lr=5e-5, desired_kl=0.1,
@@ -39,9 +49,11 @@ def ppo_cfg(E, device, precision):
         tricks=dict(mini_adv_norm=False, whole_adv_norm=False, use_state_norm=True, use_clipped_value_loss=False,
                     use_grad_clip=True, max_grad_norm=0.5),
         model=dict(action_std=0.5, action_activate="tanh", clipAction=1.0,
-                   network=dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False,
-                                point_num=N_PTS, precision=precision)),
+                   network=net or dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False,
+                                       point_num=N_PTS, precision=precision)),
     )
+    cfg.update(over)
+    return cfg
 
 
 class _Logger:
@@ -87,11 +99,12 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu"):
+def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu", budget_s=None):
     """The reference's algorithm (CPU oracle port, unmodified math) for one PPO iteration at E envs; returns
-    env·steps/s on the host cores.  Only bench.py's cpu_baseline / --impl reference legs call this.
-    device="cuda:0" runs the same eager-PyTorch restatement on the GPU (`--impl torch_gpu`: the reference's PyTorch-GPU
-    path — fp32, TF32 off, eager — as the denominator of north_star's ">= 10x" target; not a driver arm)."""
+    (env·steps/s, seconds per iteration, timed iterations).  Only bench.py's cpu_baseline / --impl reference / gpu_baseline legs
+    call this.  device="cuda:0" runs the same eager-PyTorch restatement on the GPU: the reference's PyTorch-GPU path — fp32,
+    TF32 off, eager — the denominator of north_star's ">= 10x" target.  budget_s bounds the timed region (at least one
+    timed iteration always runs)."""
     import torch
     from oracle import ppo_oracle as O
     torch.set_num_threads(threads)
@@ -122,7 +135,10 @@ def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu"):
     pool = [obs() for _ in range(T_STEPS + 1)]
     rnd = lambda *sh: dv(torch.randn(*sh, generator=g))
     times = []
+    t_start = None
     for it in range(warm + iters):
+        if it == warm:
+            t_start = time.perf_counter()
         if on_gpu:
             torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -148,29 +164,69 @@ def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu"):
         if on_gpu:
             torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
-    t = sum(times[warm:]) / max(iters, 1)
-    return E * T_STEPS / t, t
+        if budget_s is not None and it >= warm and time.perf_counter() - t_start > budget_s:
+            break
+    timed = times[warm:]
+    t = sum(timed) / max(len(timed), 1)
+    return E * T_STEPS / t, t, len(timed)
 
 
 def run_reference(args, rank):
+    """The driver's reference arm: the oracle port on all host cores; every step = one full PPO iteration at E_ref envs (an
+    intensive-metric sample of the E=4096 workload: same clouds, same hyper-parameters, minibatch min(E*T/8, 2048)).
+    E_ref is the largest of 64..512 that keeps the whole --steps/--warmup run within the budget (SURVEY §8d asks for 512)."""
     if rank != 0:
         return
     import torch
     threads = os.cpu_count() or 1
     E = args.ref_envs
-    v, t = cpu_port_iteration(E, threads, iters=args.steps, warm=args.warmup)
+    if E <= 0:
+        _, t16, _ = cpu_port_iteration(16, threads, iters=1, warm=1)        # calibrate: seconds per env of a warm iteration
+        per_env = t16 / 16
+        E = 64
+        for cand in (128, 256, 512):
+            if (args.steps + args.warmup) * per_env * cand <= args.ref_budget_s:
+                E = cand
+    v, t, n = cpu_port_iteration(E, threads, iters=args.steps, warm=args.warmup)
     line = {
         "impl": "reference", "metric": "env_steps_per_sec (encoder+PPO update)", "value": v, "unit": "env*steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"ppo + open_drawer shapes, PointNet, {N_PTS} pts x {CH} ch, A={ACT}, T={T_STEPS}, 5 epochs; "
                                f"CPU sample E={E} envs per step (minibatch {min(E * T_STEPS // 8, 2048)})"},
         "cpu_baseline": {"value": v, "unit": "env*steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full PPO iterations at E={E} (intensive metric; reference is Python/PyTorch, "
-                                   f"timed via the CPU oracle port with torch {torch.__version__} on {threads} threads)"},
+                         "sample": f"{n} full PPO iterations at E={E} after {args.warmup} warm-up (intensive metric; reference is "
+                                   f"Python/PyTorch, timed via the CPU oracle port with torch {torch.__version__} on {threads} threads)"},
         "e2e": {"value": v, "unit": "env*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU parity evidence
+PARITY_E = 8
+
+
+def _parity_run(E, shard, dev, eps_all, init=None):
+    """One PPO iteration (bf16 PointNet) on a shard of a fixed synthetic global batch; returns (init weights, final weights, log)."""
+    import torch
+    from partmanip_b200.algorithms import ppo
+    from partmanip_b200.envs import FakeVecEnv
+    torch.manual_seed(11)
+    env = FakeVecEnv(E, N_PTS * CH, ACT, dev, cloud=True, seed=99, shard=shard)
+    r = ppo(env, ppo_cfg(E, dev, "bf16", max_iterations=1), _Logger())
+    if init is not None:
+        r.actor_critic.load_state_dict(init)
+    init_sd = {k: v.clone() for k, v in r.actor_critic.state_dict().items()}
+    curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+    sr, _ = shard if shard else (0, 1)
+    last_obs, last_values = r.collect(curr, None, eps=eps_all[:, sr * E:(sr + 1) * E].contiguous().to(dev))
+    r.storage.compute_returns(last_values, r.gamma, r.lam)
+    r.update(1)
+    torch.cuda.synchronize()
+    out = {k: v.clone() for k, v in r.actor_critic.state_dict().items()}
+    log = {k: float(r.log_dict[k]) for k in ("Train/surrogate_loss", "Train/value_function_loss", "Train/kl", "Train/kl_update_count")}
+    r.release_graph()
+    return init_sd, out, log
 
 
 def main():
@@ -180,26 +236,34 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--envs", type=int, default=4096)
-    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
-    ap.add_argument("--ref-envs", type=int, default=8)
-    ap.add_argument("--cpu-baseline-envs", type=int, default=16)
+    ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32", "fp32_ffma"])
+    ap.add_argument("--ref-envs", type=int, default=0, help="reference arm: envs per step (0 = calibrate, 64..512)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    ap.add_argument("--cpu-baseline-envs", type=int, default=64)
+    ap.add_argument("--gpu-baseline-iters", type=int, default=10)
+    ap.add_argument("--gpu-baseline-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip modes.fp32 / configs (DAgger, state-MLP)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: whatever the algorithm classes print ("load teacher ckpt ...") goes to stderr
+    global _OUT
+    _OUT, sys.stdout = sys.stdout, sys.stderr
     if args.impl == "reference":
         run_reference(args, rank)
         return
     if args.impl == "torch_gpu":          # context only: eager PyTorch fp32 (TF32 off) on cuda:0, the reference's GPU path
         if rank == 0:
-            v, t = cpu_port_iteration(args.envs, os.cpu_count() or 1, iters=args.steps, warm=args.warmup, device="cuda:0")
+            v, t, n = cpu_port_iteration(args.envs, os.cpu_count() or 1, iters=args.steps, warm=args.warmup, device="cuda:0")
             print(json.dumps({"impl": "torch_gpu", "metric": "env_steps_per_sec (encoder+PPO update)", "value": v,
-                              "unit": "env*steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                              "unit": "env*steps/s", "n_gpus": 1, "steps": n, "warmup": args.warmup,
                               "ms_per_step": t * 1e3, "dtype": "f32", "data": "synthetic",
                               "config": {"workload": f"eager PyTorch restatement of the reference path on cuda:0, E={args.envs} envs x "
-                                                     f"{N_PTS} pts, fp32, TF32 off"}}), flush=True)
+                                                     f"{N_PTS} pts, fp32, TF32 off"}}), file=_OUT, flush=True)
         return
 
     import torch
@@ -208,19 +272,25 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
     from partmanip_b200 import _lib, ops
     from partmanip_b200.algorithms import ppo
     from partmanip_b200.envs import FakeVecEnv
+
+    # ---- multi-GPU parity, part 1: ONE process with world*E envs, before the process group exists (every rank, own GPU)
+    parity_ref = None
+    if world > 1:
+        g = torch.Generator().manual_seed(5)
+        eps_all = torch.randn(T_STEPS, PARITY_E * world, ACT, generator=g)
+        parity_ref = (eps_all,) + _parity_run(PARITY_E * world, None, dev, eps_all)
+        dist.init_process_group("nccl", device_id=torch.device(dev))
 
     precision = args.precision or ("bf16" if _lib.lib.pm_has_tcgen05() else "fp32")
     E, D = args.envs, N_PTS * CH
     torch.manual_seed(1234)
 
-    def make(host):
+    def make(host, prec=precision):
         env = FakeVecEnv(E, D, ACT, dev, cloud=True, channels=CH, pool=16, seed=1234 + rank, host=host)
-        runner = ppo(env, ppo_cfg(E, dev, precision), _Logger())
+        runner = ppo(env, ppo_cfg(E, dev, prec), _Logger())
         return env, runner
 
     def iteration(runner, curr):
@@ -256,64 +326,82 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, ops.launch_count() - calls0, clocks
 
-    # ---- device-resident arm (value)
-    env, runner = make(host=False)
-    ms_step, launches, clocks = timed(runner, env, args.steps, args.warmup, rank == 0)
-    value = E * T_STEPS * world / (ms_step * 1e-3)
+    def kernel_ms(fn, reps=16, warm=3):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(reps):
+            fn(i)
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
 
-    # ---- dominant kernel: PointNet encoder forward on one 2048-cloud minibatch, timed live with CUDA events
-    B = min(2048, E * T_STEPS)
-    obs_flat = runner.storage.observations.view(-1, D)
-    nslices = obs_flat.shape[0] // B
-    actor = runner.actor_critic.actor
-    enc = actor.runner.enc_params()
-    feat = torch.empty(B, 512, device=dev)
-    am = torch.empty(B, 512, device=dev, dtype=torch.int32)
-    for i in range(3):
-        ops.pointnet_encode_forward(obs_flat[(i % nslices) * B:(i % nslices + 1) * B], N_PTS, CH, enc, "tanh", precision, feat, None, am, None)
-    torch.cuda.synchronize()
-    reps = 16
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for i in range(reps):   # successive launches read different 25 MB slices of the 403 MB buffer (> L2)
-        ops.pointnet_encode_forward(obs_flat[(i % nslices) * B:(i % nslices + 1) * B], N_PTS, CH, enc, "tanh", precision, feat, None, am, None)
-    k1.record()
-    torch.cuda.synchronize()
-    enc_ms = k0.elapsed_time(k1) / reps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0)
-    achieved_tf = B * ENC_FLOPS_PER_CLOUD / (enc_ms * 1e-3) / 1e12
-    # encoder-forward launches per iteration: T rollout steps x (actor + critic) + the last-value critic pass, each over
-    # E clouds (E/B launch-equivalents of B clouds), + 2 networks x 5 epochs x (E*T/B) minibatches
-    enc_equiv_per_iter = (T_STEPS * 2 + 1) * (E / B) + 2 * 5 * (E * T_STEPS // B)
-    # companion kernel: encoder backward on the same minibatch
-    grads = [torch.empty_like(t) for t in enc]
-    dfeat = torch.randn(B, 512, device=dev) * 0.01
-    for i in range(2):
-        ops.pointnet_encode_backward(obs_flat[:B], N_PTS, CH, enc, "tanh", dfeat, am, grads, precision=precision)
-    k0.record()
-    for i in range(reps):
-        ops.pointnet_encode_backward(obs_flat[(i % nslices) * B:(i % nslices + 1) * B], N_PTS, CH, enc, "tanh", dfeat, am, grads,
-                                     precision=precision)
-    k1.record()
-    torch.cuda.synchronize()
-    bwd_ms = k0.elapsed_time(k1) / reps
-    # DRAM traffic of the forward kernel per launch from the committed `ncu --set full` capture
-    # (profiles/r01_fwd_r01c_metrics.txt: dram__bytes_read.sum 25.57 MB, dram__bytes_write.sum ~0: the 8 MB of outputs
-    # stay in the 126 MB L2) — the algorithmic input is B*N*C*4 = 25.17 MB
-    traffic = 25571072 if (precision == "bf16" and B == 2048) else None
-    roofline = {"bound": "tensor", "kernel": "pointnet encoder forward (%s), %d clouds x %d pts per launch" % (precision, B, N_PTS),
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if peaks else "fallback 1.59 PF, of fallback",
-                "traffic": traffic, "algorithmic_bytes": B * N_PTS * CH * 4, "algorithmic_flops": B * ENC_FLOPS_PER_CLOUD,
-                "ms_per_launch": enc_ms, "share_of_step": enc_ms * enc_equiv_per_iter / ms_step,
-                "hbm_frac_for_transparency": (B * N_PTS * CH * 4 / (enc_ms * 1e-3) / 1e9) / peaks.get("hbm_gbs", 6650.0),
-                "companion": {"kernel": "pointnet encoder backward (%s), same minibatch" % precision, "ms_per_launch": bwd_ms,
-                              "share_of_step": bwd_ms * 2 * 5 * (E * T_STEPS // B) / ms_step}}
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst), of measured" if peaks else "fallback 1.59 PF, of fallback"
+
+    def encoder_roofline(runner, prec, ms_step):
+        """Dominant kernel (encoder forward) and its companion (encoder backward) on one 2048-cloud minibatch, timed live with CUDA
+        events; successive launches read different 25 MB slices of the 403 MB rollout buffer (> L2)."""
+        B = min(2048, E * T_STEPS)
+        obs_flat = runner.storage.observations.view(-1, D)
+        nsl = obs_flat.shape[0] // B
+        enc = runner.actor_critic.actor.runner.enc_params()
+        feat = torch.empty(B, 512, device=dev)
+        am = torch.empty(B, 512, device=dev, dtype=torch.int32)
+        sl = lambda i: obs_flat[(i % nsl) * B:(i % nsl + 1) * B]
+        reps = 16 if prec != "fp32_ffma" else 3
+        enc_ms = kernel_ms(lambda i: ops.pointnet_encode_forward(sl(i), N_PTS, CH, enc, "tanh", prec, feat, None, am, None), reps)
+        grads = [torch.empty_like(t) for t in enc]
+        dfeat = torch.randn(B, 512, device=dev) * 0.01
+        bwd_ms = kernel_ms(lambda i: ops.pointnet_encode_backward(sl(i), N_PTS, CH, enc, "tanh", dfeat, am, grads, precision=prec), reps)
+        srt = am.sort(dim=1)[0]
+        uniq = int((srt[:, 1:] != srt[:, :-1]).sum()) + B                 # unique critical points of the minibatch
+        achieved = B * ENC_FLOPS_PER_CLOUD / (enc_ms * 1e-3) / 1e12
+        # what the tensor pipe executes per algorithmic flop: 1 MMA (bf16) or 3 (split fp16) per product of layers 2-3
+        mma_mult = {"bf16": 1, "fp32": 3}.get(prec)
+        # encoder-forward launch-equivalents per iteration: T rollout steps x (actor + critic) + the last-value critic pass, each
+        # over E clouds (E/B launches of B clouds), + 2 networks x 5 epochs x (E*T/B) minibatches
+        fwd_per_iter = (T_STEPS * 2 + 1) * (E / B) + 2 * 5 * (E * T_STEPS // B)
+        bwd_per_iter = 2 * 5 * (E * T_STEPS // B)
+        rows = B * 512
+        roof = {"bound": "tensor", "kernel": "pointnet encoder forward (%s), %d clouds x %d pts per launch" % (prec, B, N_PTS),
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
+                "traffic": 25571072 if (prec == "bf16" and B == 2048) else None,
+                "traffic_source": "ncu --set full capture committed under profiles/ (dram__bytes_read.sum + write.sum of one launch); "
+                                  "not measured live by bench.py" if (prec == "bf16" and B == 2048) else None,
+                "algorithmic_bytes": B * N_PTS * CH * 4, "algorithmic_flops": B * ENC_FLOPS_PER_CLOUD,
+                "ms_per_launch": enc_ms, "share_of_step": enc_ms * fwd_per_iter / ms_step,
+                "hbm_frac_for_transparency": (B * N_PTS * CH * 4 / (enc_ms * 1e-3) / 1e9) / peaks.get("hbm_gbs", 6650.0)}
+        if mma_mult and mma_mult > 1:
+            roof["executed_mma_tflops"] = achieved * mma_mult
+            roof["executed_frac_of_bf16_peak"] = achieved * mma_mult / peak_tf
+            roof["note"] = "frac counts ALGORITHMIC flops; every product runs as %d fp16 MMAs (hi.hi + lo.hi + hi.lo)" % mma_mult
+        comp = {"kernel": "pointnet encoder backward (%s), same minibatch" % prec, "ms_per_launch": bwd_ms,
+                "share_of_step": bwd_ms * bwd_per_iter / ms_step, "unit": "TFLOP/s", "peak": peak_tf,
+                "unique_critical_points": uniq, "rows_executed": rows if prec == "bf16" else uniq,
+                "algorithmic_flops_unique_points": uniq * BWD_FLOPS_PER_ROW}
+        uniq_tf = uniq * BWD_FLOPS_PER_ROW / (bwd_ms * 1e-3) / 1e12
+        comp["achieved_unique"] = uniq_tf
+        comp["frac_unique"] = uniq_tf / peak_tf
+        if prec == "bf16":       # the fused kernel treats every (cloud, channel) pair as a row: rows/uniq x duplicate work
+            ex_tf = rows * BWD_FLOPS_PER_ROW / (bwd_ms * 1e-3) / 1e12
+            comp["achieved_executed"] = ex_tf
+            comp["frac_executed"] = ex_tf / peak_tf
+        roof["companion"] = comp
+        return roof
+
+    # ---- device-resident arm (value)
+    env, runner = make(host=False)
+    ms_step, launches, clocks = timed(runner, env, args.steps, args.warmup, rank == 0)
+    value = E * T_STEPS * world / (ms_step * 1e-3)
+    roofline = encoder_roofline(runner, precision, ms_step)
 
     # ---- end-to-end arm: host-resident observations, H2D copy of every step's obs + D2H of the actions inside the timed region
     e2e = None
@@ -329,17 +417,84 @@ def main():
         e2e = {"value": E * T_STEPS * world / (ms_e2e * 1e-3), "unit": "env*steps/s",
                "h2d_bytes_per_step": int(env_h.h2d_bytes / iters_run), "d2h_bytes_per_step": int(env_h.d2h_bytes / iters_run),
                "ms_per_step": ms_e2e}
+        del env_h, runner_h
 
-    # ---- CPU baseline (oracle port) on rank 0, N=1 only
-    cpu_baseline = None
+    # ---- multi-GPU parity, part 2: world ranks x PARITY_E envs against the single-process run
+    multi_gpu_parity = None
+    if world > 1:
+        runner.release_graph()
+        eps_all, init_sd, ref_sd, ref_log = parity_ref
+        _, sd, log = _parity_run(PARITY_E, (rank, world), dev, eps_all, init=init_sd)
+        flat = torch.cat([v.reshape(-1) for v in sd.values()])
+        ref0 = flat.clone()
+        dist.broadcast(ref0, 0)
+        same = torch.tensor([1 if torch.equal(flat, ref0) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        lr, steps40 = 5e-5, 40
+        worst = max(float((sd[k] - ref_sd[k]).abs().max()) for k in sd) / (lr * steps40)
+        multi_gpu_parity = {
+            "workload": f"one PPO iteration, PointNet bf16, {world} ranks x {PARITY_E} envs vs ONE process with {world * PARITY_E} envs "
+                        "(same synthetic global batch, same initial weights, same exploration noise)",
+            "replicas_bit_identical_across_ranks": bool(int(same)),
+            "loss_vs_1proc": {k: {"ranks": log[k], "one_process": ref_log[k]} for k in log},
+            "max_rel_diff_losses": max(abs(log[k] - ref_log[k]) / max(1.0, abs(ref_log[k])) for k in log),
+            "worst_weight_diff_over_40lr": worst,
+        }
+
+    modes, configs, gpu_baseline, cpu_baseline = None, None, None, None
+    extras = rank == 0 and world == 1 and not args.no_extras
+    if extras:
+        runner.release_graph()
+        del runner
+        torch.cuda.empty_cache()
+        # ---- the reference's precision: same workload, precision fp32 (split-operand tcgen05 kernels, 1e-4 parity gate)
+        if precision == "bf16":
+            env32, r32 = make(host=False, prec="fp32")
+            ms32, _, _ = timed(r32, env32, max(2, min(args.steps, 3)), 2, False)
+            roof32 = encoder_roofline(r32, "fp32", ms32)
+            modes = {"fp32": {"value": E * T_STEPS / (ms32 * 1e-3), "unit": "env*steps/s", "ms_per_step": ms32, "dtype": "f32",
+                              "parity_gate": "1e-4 (north_star fp32)", "roofline": roof32}}
+            r32.release_graph()
+            del env32, r32
+            torch.cuda.empty_cache()
+        configs = {}
+        # ---- BASELINE config 4: DAgger, state expert -> vision student, 2048 envs x 2048-pt clouds, random sampler
+        try:
+            configs["dagger_2048x2048"] = bench_dagger(dev, precision)
+        except Exception as e:  # pragma: no cover - keep the headline line alive
+            configs["dagger_2048x2048"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        # ---- the shipped state policy: ppo + MLP 53 -> 512^3 -> 10 at E = 2048 (cfg/algos/ppo.yaml)
+        try:
+            configs["state_mlp_2048"] = bench_state_mlp(dev, peak_tf, peak_src, kernel_ms)
+        except Exception as e:  # pragma: no cover
+            configs["state_mlp_2048"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- the reference's PyTorch-GPU path on this GPU (eager fp32, TF32 off): the ">= 10x" denominator
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            v, t, n = cpu_port_iteration(E, os.cpu_count() or 1, iters=args.gpu_baseline_iters, warm=3, device=dev,
+                                         budget_s=args.gpu_baseline_budget_s)
+            gpu_baseline = {"value": v, "unit": "env*steps/s", "ms_per_step": t * 1e3, "steps": n, "warmup": 3, "dtype": "f32",
+                            "kind": "port", "what": "eager PyTorch restatement of the reference's encoder+PPO path (oracle port) on the "
+                                                    "same GPU: fp32, TF32 off, default stream, same E / clouds / hyper-parameters",
+                            "speedup_bf16_mode": value / v,
+                            "speedup_fp32_mode": (modes["fp32"]["value"] / v) if modes else (value / v if precision != "bf16" else None)}
+        except Exception as e:  # pragma: no cover
+            gpu_baseline = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- CPU baseline (oracle port) on rank 0, N=1 only: one warm-up + timed iterations at E=64
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         Ec = args.cpu_baseline_envs
-        v, t = cpu_port_iteration(Ec, threads, iters=1, warm=0)
+        v, t, n = cpu_port_iteration(Ec, threads, iters=2, warm=1, budget_s=40.0)
         cpu_baseline = {"value": v, "unit": "env*steps/s", "cores": threads, "kind": "port",
-                        "sample": f"1 full PPO iteration at E={Ec} envs x {N_PTS} pts ({t:.1f} s) with the CPU oracle port"}
+                        "sample": f"{n} full PPO iteration(s) at E={Ec} envs x {N_PTS} pts after 1 warm-up ({t:.1f} s each) with the CPU oracle port"}
 
     if rank == 0:
+        B = min(2048, E * T_STEPS)
         line = {
             "metric": "env_steps_per_sec (encoder+PPO update)", "value": value, "unit": "env*steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -349,14 +504,116 @@ def main():
                        "envs_per_gpu": E, "precision": precision, "cache": "inputs 403 MB rollout buffer > 126 MB L2",
                        "parallelism": f"env-sharded x{world}" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "modes": modes, "gpu_baseline": gpu_baseline, "configs": configs, "multi_gpu_parity": multi_gpu_parity,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         # leave without tearing NCCL down: captured graphs hold NCCL work objects and destroy_process_group() can block on them
-        runner.release_graph()
         barrier()
-        sys.stdout.flush()
+        _OUT.flush()
+        sys.stderr.flush()
         os._exit(0)
+
+
+def bench_dagger(dev, precision):
+    """BASELINE config 4 at full size on one GPU: E = 2048 envs x 2048-pt clouds (D = 6144), vision student (PointNet), frozen
+    state teacher (MLP 53 -> 512^3 -> 10), ring buffer of 16 steps (32768 rows, 805 MB), random sampler, n_steps = 1,
+    2 epochs x 16 minibatches of 2048 per iteration (cfg/algos/dagger_tsdf.yaml hyper-parameters; PointNet instead of the
+    Conv3D student).  One step = rollout step (student acts, both observations stored) + update; env·steps/s = E / time."""
+    import torch
+    from oracle import ppo_oracle as O
+    from partmanip_b200.algorithms import dagger
+    from partmanip_b200.envs import FakeVecEnv
+    E, NP, A, Dt = 2048, 2048, 10, 53
+    D = NP * CH
+    g = torch.Generator().manual_seed(21)
+    tea_cfg = dict(action_std=0.5, action_activate="tanh", clipAction=1.0, network=dict(name="MLP", hid_dim=[512, 512, 512], activation="tanh"))
+    sd = {f"actor.{k}": v for k, v in O.mlp_init(Dt, A, [512, 512, 512], gen=g).items()}
+    sd.update({f"critic.{k}": v for k, v in O.mlp_init(Dt, 1, [512, 512, 512], gen=g).items()})
+    sd["log_std"] = torch.full((A,), -0.69)
+    os.makedirs("/tmp/pm_b200_bench", exist_ok=True)
+    path = "/tmp/pm_b200_bench/teacher.pth"
+    torch.save(dict(obs_mode="state", model_cfg=tea_cfg, model_state_dict=sd, tricks=dict(use_state_norm=False)), path)
+    net = dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, point_num=NP, precision=precision)
+    cfg = dict(num_envs=E, obs_mode="obs", max_iterations=10 ** 9, n_steps=1, n_updates=2, n_minibatches=16, device=dev, buf_size=16,
+               reward_reset=False, add_proprio_obs=False, offline_data_pth=None, eval_round=1, eval_frequence=10 ** 9,
+               save_frequence=10 ** 9, test_only=False, save_pose=False, save_video=False, lr_schedule="fixed", lr=5e-5,
+               teacher=path, resume=None, pretrain=None, sampler="random",
+               model=dict(action_std=0.1, action_activate="tanh", clipAction=1.0, network=net))
+    env = FakeVecEnv(E, D, A, dev, cloud=True, channels=CH, pool=8, seed=77, extra_obs={"state": Dt})
+    r = dagger(env, cfg, _Logger())
+    stu, tea = r._reset_env()
+    for _ in range(16):                                   # fill the ring
+        stu, tea, _ = r._collect(stu, tea)
+    for _ in range(2):
+        stu, tea, _ = r._collect(stu, tea)
+        r.update(1)
+    torch.cuda.synchronize()
+    iters = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        stu, tea, _ = r._collect(stu, tea)
+        r.update(1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": E / (ms * 1e-3), "unit": "env*steps/s", "ms_per_step": ms, "steps": iters, "warmup": 2, "dtype": precision,
+            "workload": f"dagger: {E} envs x {NP}-pt clouds, buffer 16 x {E} rows, random sampler, 2 epochs x 16 minibatches of 2048, "
+                        "teacher MLP 53->512^3->10; one step = 1 env step for all envs + update",
+            "dagger_loss": float(r.log_dict["Train/dagger_loss"])}
+
+
+def bench_state_mlp(dev, peak_tf, peak_src, kernel_ms):
+    """The configuration the shipped `--algocfg ppo --taskcfg open_drawer` runs (cfg/algos/ppo.yaml: E = 2048, MLP 53 -> 512^3 ->
+    10, tanh): full PPO iterations in the fp32 parity mode (three-term bf16 split on tcgen05) and in bf16, and the roofline of
+    its dominant GEMM (2048 x 512 x 512 fc layer) against the measured bf16 tensor peak."""
+    import torch
+    from partmanip_b200 import ops
+    from partmanip_b200.algorithms import ppo
+    from partmanip_b200.envs import FakeVecEnv
+    E, D, A = 2048, 53, 10
+    out = {"workload": f"ppo + state obs: {E} envs, MLP {D}->512^3->{A} (cfg/algos/ppo.yaml), T={T_STEPS}, 5 epochs x 8 minibatches of 2048"}
+    for prec in ("fp32", "bf16", "fp32_ffma"):
+        net = dict(name="MLP", hid_dim=[512, 512, 512], activation="tanh", precision=prec)
+        env = FakeVecEnv(E, D, A, dev, cloud=False, pool=16, seed=5)
+        r = ppo(env, ppo_cfg(E, dev, prec, net=net), _Logger())
+        curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+
+        def it(curr):
+            last_obs, last_values = r.collect(curr, None)
+            r.storage.compute_returns(last_values, r.gamma, r.lam)
+            r.update(1)
+            r.storage.clear()
+            return ops.copy_rows(last_obs, r.storage.obs_slot())
+        for _ in range(3):
+            curr = it(curr)
+        torch.cuda.synchronize()
+        iters = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            curr = it(curr)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[prec] = {"value": E * T_STEPS / (ms * 1e-3), "unit": "env*steps/s", "ms_per_step": ms, "steps": iters, "warmup": 3}
+        r.release_graph()
+    # dominant GEMM: one 512 x 512 fc layer over a 2048-row minibatch (forward), rotating over 8 input buffers
+    M, N, K = 2048, 512, 512
+    xs = [torch.randn(M, K, device=dev) for _ in range(8)]
+    W, b = torch.randn(N, K, device=dev) / K ** 0.5, torch.zeros(N, device=dev)
+    y = torch.empty(M, N, device=dev)
+    roof = {}
+    for prec, mult in (("bf16", 1), ("fp32", 6)):
+        ms = kernel_ms(lambda i: ops.linear_forward_tc(xs[i % 8], W, b, "tanh", prec, out=y), 50, 5)
+        tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        roof[prec] = {"bound": "tensor", "kernel": f"fc {K}->{N} forward over {M} rows on tcgen05 ({prec})", "ms_per_launch": ms,
+                      "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "peak_source": peak_src,
+                      "executed_mma_tflops": tf * mult,
+                      "note": "1 GFLOP per launch on 64 CTAs: latency-bound (fp32 operands are converted to bf16 images in the kernel)"}
+    out["roofline"] = roof
+    return out
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ def _run(*args):
 
 
 def test_reference_arm_prints_the_contract_line():
-    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-envs", "8")   # (default: calibrated E in 64..512)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["higher_is_better"] is True and line["scaling"] == "weak" and line["vs_baseline"] is None
