@@ -100,14 +100,29 @@ __device__ __forceinline__ void store_tile(const TileRegs& r, uint8_t* base /* P
   }
 }
 
+// PARTS = 1: two 32 KB stages (three CTAs per SM).  PARTS = 3: ONE 96 KB stage, so that two CTAs share an SM and overlap each
+// other's load / convert / MMA / epilogue phases — measured on the 250k x 256 x 128 layers of the encoder backward, where every
+// CTA has only two k-blocks and an in-CTA pipeline never fills: 633 us with two stages and one CTA per SM.
 template <int PARTS> struct SmemPlan {
+  static constexpr int NSTG = PARTS == 1 ? 2 : 1;
   static constexpr uint32_t STAGE = 2u * PARTS * IMG_BYTES;       // A parts then B parts
-  static constexpr uint32_t BAR = 2u * STAGE;                     // 3 mbarriers + tmem slot
+  static constexpr uint32_t BAR = NSTG * STAGE;                   // NSTG + 1 mbarriers + tmem slot
   static constexpr uint32_t TOTAL = BAR + 64;
 };
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the MUFU pipe: absolute error <= 4e-7 (tanhf costs ~25 instructions per element)
+__device__ __forceinline__ float act_fwd_fast(int act, float x) {
+  if (act == PM_ACT_TANH) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
+  }
+  return pm_act_fwd(act, x);
+}
+
 template <int PARTS, int EPI, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GT_THREADS, 1)
+__global__ void __launch_bounds__(GT_THREADS, 2)
 gemm_tc_kernel(const GemmTcP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using Plan = SmemPlan<PARTS>;
@@ -130,11 +145,12 @@ gemm_tc_kernel(const GemmTcP p) {
   }
   const int nkb = (k_end - k_begin + TBK - 1) / TBK;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Plan::BAR + 32);
-  auto bar = [&](int i) { return sbase + Plan::BAR + 8u * i; };    // 0,1: stage free | 2: accumulator complete
+  constexpr int NSTG = Plan::NSTG;
+  auto bar = [&](int i) { return sbase + Plan::BAR + 8u * i; };    // 0..NSTG-1: stage free | NSTG: accumulator complete
 
   if ((sbase & 1023u) != 0 && tid == 0) err_report(p.err, 910);
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) mbar_init(bar(i), 1);
+    for (int i = 0; i <= NSTG; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -154,9 +170,9 @@ gemm_tc_kernel(const GemmTcP p) {
     load_tile<B_MN>(rb, p.B, p.ldb, n0, k_begin, p.N, k_end, tid);
   }
   for (int kb = 0; kb < nkb && ok; ++kb) {
-    const int s = kb & 1;
-    if (kb >= 2) {                               // the MMAs that read this stage two blocks ago are done
-      ok = mbar_wait(bar(s), ((kb >> 1) - 1) & 1, p.err, 911);
+    const int s = kb % NSTG;
+    if (kb >= NSTG) {                            // the MMAs that read this stage NSTG blocks ago are done
+      ok = mbar_wait(bar(s), ((kb / NSTG) - 1) & 1, p.err, 911);
       if (!ok) break;
     }
     uint8_t* st = smem + s * Plan::STAGE;
@@ -186,11 +202,11 @@ gemm_tc_kernel(const GemmTcP p) {
         }
       }
       umma_commit_1cta(bar(s));                  // frees the stage when these MMAs have read it
-      if (kb == nkb - 1) umma_commit_1cta(bar(2));
+      if (kb == nkb - 1) umma_commit_1cta(bar(NSTG));
     }
     __syncwarp();
   }
-  if (ok && nkb > 0) ok = mbar_wait(bar(2), 0, p.err, 912);
+  if (ok && nkb > 0) ok = mbar_wait(bar(NSTG), 0, p.err, 912);
   if (ok) {
     tc_fence_after();
     // ---- epilogue: warp w reads TMEM lanes (w & 3) * 32 .. +32 (rows), columns (w >> 2) * 64 .. +64
@@ -219,7 +235,7 @@ gemm_tc_kernel(const GemmTcP p) {
           if (col < p.N) {
             if (EPI == EPI_FWD) {
               if (p.bias) x += __ldg(p.bias + col);
-              x = pm_act_fwd(p.act, x);
+              x = act_fwd_fast(p.act, x);
             } else if (EPI == EPI_DX) {
               if (p.act != PM_ACT_NONE) x *= pm_act_bwd(p.act, __ldg(p.aux + (int64_t)row * p.ldaux + col));
             }
@@ -254,27 +270,46 @@ __global__ void splitk_reduce_tc_kernel(const float* __restrict__ partial, int s
   out[i] = t;
 }
 
-// db partials: part[split][n] = sum over the split's rows of dY[row, n]   (rows limited by *lim_dev)
-__global__ void __launch_bounds__(128)
+// db partials: part[split][n] = sum over the split's rows of dY[row, n]   (rows limited by *lim_dev).  A CTA takes 128 columns
+// (32 lanes x float4) of its split's rows, eight rows at a time (one per warp) with two loads in flight per thread, then folds the
+// eight row-lanes in shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
 colsum_split_kernel(const float* __restrict__ dY, int64_t ld, int rows, int N, const int32_t* __restrict__ lim_dev, int rows_per_split,
                     float* __restrict__ part) {
-  const int n = blockIdx.x * 128 + threadIdx.x;
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + lane * 4;
   if (lim_dev) {
     rows = min(rows, *lim_dev);
     rows_per_split = ((rows + (int)gridDim.y - 1) / (int)gridDim.y + TBK - 1) / TBK * TBK;
   }
   const int r0 = min(rows, (int)blockIdx.y * rows_per_split), r1 = min(rows, r0 + rows_per_split);
-  if (n >= N) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    a0 += __ldg(dY + (int64_t)r * ld + n);
-    a1 += __ldg(dY + (int64_t)(r + 1) * ld + n);
-    a2 += __ldg(dY + (int64_t)(r + 2) * ld + n);
-    a3 += __ldg(dY + (int64_t)(r + 3) * ld + n);
+  const bool vec = (n + 4 <= N) && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dY) & 15u) == 0);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  auto ld4 = [&](int r) -> float4 {
+    const float* p = dY + (int64_t)r * ld + n;
+    if (vec) return __ldg(reinterpret_cast<const float4*>(p));
+    return make_float4(n < N ? __ldg(p) : 0.f, n + 1 < N ? __ldg(p + 1) : 0.f, n + 2 < N ? __ldg(p + 2) : 0.f, n + 3 < N ? __ldg(p + 3) : 0.f);
+  };
+  int r = r0 + w;
+  for (; r + 8 < r1; r += 16) {
+    const float4 u = ld4(r), v = ld4(r + 8);
+    a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+    b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
   }
-  for (; r < r1; ++r) a0 += __ldg(dY + (int64_t)r * ld + n);
-  part[(int64_t)blockIdx.y * N + n] = (a0 + a1) + (a2 + a3);
+  if (r < r1) { const float4 u = ld4(r); a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w; }
+  red[w][lane] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  __syncthreads();
+  if (w == 0) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 u = red[k][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    float* o = part + (int64_t)blockIdx.y * N + n;
+    if (n < N) o[0] = t.x;
+    if (n + 1 < N) o[1] = t.y;
+    if (n + 2 < N) o[2] = t.z;
+    if (n + 3 < N) o[3] = t.w;
+  }
 }
 
 inline int dw_splits_tc(int Mrows, int N, int K) {
@@ -349,7 +384,7 @@ int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const flo
     if (rc) return rc;
     splitk_reduce_tc_kernel<<<pm_cdiv((int64_t)N * K, 256), 256, 0, st>>>(part, splits, (int64_t)N * K, dW);
     if (db) {
-      colsum_split_kernel<<<dim3(pm_cdiv(N, 128), splits), 128, 0, st>>>(dpre, lddpre, M, N, m_dev, kps, dbpart);
+      colsum_split_kernel<<<dim3(pm_cdiv(N, 128), splits), 256, 0, st>>>(dpre, lddpre, M, N, m_dev, kps, dbpart);
       splitk_reduce_tc_kernel<<<pm_cdiv(N, 256), 256, 0, st>>>(dbpart, splits, N, db);
     }
   }

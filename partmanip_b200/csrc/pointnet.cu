@@ -357,22 +357,94 @@ crit_layer1_kernel(const float* __restrict__ Xc, int C, const float* __restrict_
   }
 }
 
-// dPre2[r,k] = (sum_{c in chan(r)} dfeat[b,c] W3[c,k]  [+ gm[b,k]]) * act'(H2c[r,k])
+// dPre2[r,k] = (sum_{c in chan(r)} dfeat[b,c] W3[c,k]  [+ gm[b,k]]) * act'(H2c[r,k]);
+// four rows per CTA (64 threads x float4 over k per row) so that each SM keeps many W3-row gathers (L2) in flight; per element the
+// channels are summed in ascending order (deterministic)
 __global__ void __launch_bounds__(256)
-crit_dh2_kernel(const float* __restrict__ dfeat, int64_t lddf, const float* __restrict__ W3,
-                const float* __restrict__ H2c, const int32_t* __restrict__ row_b, const int32_t* __restrict__ row_cbeg,
-                const int32_t* __restrict__ row_ccnt, const int32_t* __restrict__ chan_sorted,
-                const float* __restrict__ gm, int act, const int32_t* __restrict__ r_dev, float* __restrict__ dPre2) {
-  const int R = *r_dev, k = threadIdx.x;
-  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+crit_dh2_v4_kernel(const float* __restrict__ dfeat, int64_t lddf, const float* __restrict__ W3,
+                   const float* __restrict__ H2c, const int32_t* __restrict__ row_b, const int32_t* __restrict__ row_cbeg,
+                   const int32_t* __restrict__ row_ccnt, const int32_t* __restrict__ chan_sorted,
+                   const float* __restrict__ gm, int act, const int32_t* __restrict__ r_dev, float* __restrict__ dPre2) {
+  const int R = *r_dev, sub = threadIdx.x >> 6, l = threadIdx.x & 63;
+  for (int r = blockIdx.x * 4 + sub; r < R; r += gridDim.x * 4) {
     const int b = row_b[r], beg = row_cbeg[r], q = row_ccnt[r];
-    float a = gm ? gm[(int64_t)b * 256 + k] : 0.f;
-    for (int j = 0; j < q; ++j) {
-      const int c = chan_sorted[beg + j];
-      a = fmaf(dfeat[(int64_t)b * lddf + c], __ldg(W3 + (int64_t)c * 256 + k), a);
+    float4 a = gm ? __ldg(reinterpret_cast<const float4*>(gm + (int64_t)b * 256) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = 0;
+    for (; j + 2 <= q; j += 2) {
+      const int c0 = chan_sorted[beg + j], c1 = chan_sorted[beg + j + 1];
+      const float g0 = dfeat[(int64_t)b * lddf + c0], g1 = dfeat[(int64_t)b * lddf + c1];
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W3 + (int64_t)c0 * 256) + l);
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W3 + (int64_t)c1 * 256) + l);
+      a.x = fmaf(g0, w0.x, a.x); a.y = fmaf(g0, w0.y, a.y); a.z = fmaf(g0, w0.z, a.z); a.w = fmaf(g0, w0.w, a.w);
+      a.x = fmaf(g1, w1.x, a.x); a.y = fmaf(g1, w1.y, a.y); a.z = fmaf(g1, w1.z, a.z); a.w = fmaf(g1, w1.w, a.w);
     }
-    dPre2[(int64_t)r * 256 + k] = a * pm_act_bwd(act, H2c[(int64_t)r * 256 + k]);
+    if (j < q) {
+      const int c0 = chan_sorted[beg + j];
+      const float g0 = dfeat[(int64_t)b * lddf + c0];
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W3 + (int64_t)c0 * 256) + l);
+      a.x = fmaf(g0, w0.x, a.x); a.y = fmaf(g0, w0.y, a.y); a.z = fmaf(g0, w0.z, a.z); a.w = fmaf(g0, w0.w, a.w);
+    }
+    const float4 h = *(reinterpret_cast<const float4*>(H2c + (int64_t)r * 256) + l);
+    *(reinterpret_cast<float4*>(dPre2 + (int64_t)r * 256) + l) =
+        make_float4(a.x * pm_act_bwd(act, h.x), a.y * pm_act_bwd(act, h.y), a.z * pm_act_bwd(act, h.z), a.w * pm_act_bwd(act, h.w));
   }
+}
+
+// layer-1 gradients over the compacted rows: part[slab][ch][0..C-1] = sum_r dPre1[r,ch] * Xc[r,c], part[slab][ch][CMAX] = sum_r dPre1[r,ch].
+// 256 threads = 2 row-lanes x 128 h1 channels; rows dealt to CTAs in contiguous slabs; four rows in flight per thread.
+constexpr int DW1_SLABS = 8 * PM_NUM_SMS;
+__global__ void __launch_bounds__(256)
+crit_dw1_kernel(const float* __restrict__ dPre1, const float* __restrict__ Xc, int C, const int32_t* __restrict__ r_dev,
+                float* __restrict__ part) {
+  __shared__ float red[128][CMAX + 1];
+  const int R = *r_dev, ch = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int per = ((R + (int)gridDim.x - 1) / (int)gridDim.x + 7) / 8 * 8;
+  const int r0 = min(R, (int)blockIdx.x * per), r1 = min(R, r0 + per);
+  float acc[CMAX + 1];
+#pragma unroll
+  for (int c = 0; c <= CMAX; ++c) acc[c] = 0.f;
+  int r = r0 + half;
+  for (; r + 6 < r1; r += 8) {                                  // rows r, r+2, r+4, r+6 of this row-lane
+    float d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = dPre1[(int64_t)(r + 2 * u) * 128 + ch];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) acc[c] = fmaf(d[u], __ldg(Xc + (int64_t)(r + 2 * u) * C + c), acc[c]);
+      acc[CMAX] += d[u];
+    }
+  }
+  for (; r < r1; r += 2) {
+    const float d = dPre1[(int64_t)r * 128 + ch];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) acc[c] = fmaf(d, __ldg(Xc + (int64_t)r * C + c), acc[c]);
+    acc[CMAX] += d;
+  }
+  if (half == 1) {
+#pragma unroll
+    for (int c = 0; c <= CMAX; ++c) red[ch][c] = acc[c];
+  }
+  __syncthreads();
+  if (half == 0) {
+    float* out = part + ((int64_t)blockIdx.x * 128 + ch) * (CMAX + 1);
+#pragma unroll
+    for (int c = 0; c <= CMAX; ++c) out[c] = acc[c] + red[ch][c];
+  }
+}
+// fixed-order sum of the slabs -> dW1 (128, C) and db1 (128): one warp per output, lanes stride the slabs, shuffle tree
+__global__ void __launch_bounds__(256)
+crit_dw1_reduce_kernel(const float* __restrict__ part, int slabs, int C, float* __restrict__ dW1, float* __restrict__ db1) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= 128 * (CMAX + 1)) return;
+  const int ch = i / (CMAX + 1), c = i % (CMAX + 1);
+  if (c >= C && c != CMAX) return;
+  float t = 0.f;
+  for (int s = lane; s < slabs; s += 32) t += part[((int64_t)s * 128 + ch) * (CMAX + 1) + c];
+  t = pm_warp_sum(t);
+  if (lane == 0) { if (c == CMAX) db1[ch] = t; else dW1[ch * C + c] = t; }
 }
 
 // dW3 partial over a slab of clouds: part[slab][c][k] = sum_{b in slab} dfeat[b,c] * H2c[slot[b,c]][k]
@@ -486,6 +558,8 @@ inline BwdWs carve_bwd(void* ws, int B, int N, int C, int with_mean) {
   size_t l3 = pm_linear_backward_tc_ws_bytes(rm, 256, 128);
   w.lin_bytes = l1 > l2 ? l1 : l2;
   if (l3 > w.lin_bytes) w.lin_bytes = l3;
+  const size_t l4 = (size_t)DW1_SLABS * 128 * (CMAX + 1) * sizeof(float);
+  if (l4 > w.lin_bytes) w.lin_bytes = l4;
   w.lin = (float*)take(w.lin_bytes);
   w.total = off;
   return w;
@@ -574,8 +648,8 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
   if (rc) return rc;
   // 3. layer 3: dPre2 rows and dW3/db3
   if (with_mean) mean_gm_kernel<<<B, 256, 0, st>>>(dfeat_mean, lddf, p->W3, 1.f / (float)N, w.gm);
-  crit_dh2_kernel<<<grid_rows, 256, 0, st>>>(dfeat, lddf, p->W3, w.H2c, w.row_b, w.row_cbeg, w.row_ccnt, w.chan_sorted,
-                                              with_mean ? w.gm : nullptr, act, w.r_dev, w.dPre2);
+  crit_dh2_v4_kernel<<<grid_rows, 256, 0, st>>>(dfeat, lddf, p->W3, w.H2c, w.row_b, w.row_cbeg, w.row_ccnt, w.chan_sorted,
+                                                 with_mean ? w.gm : nullptr, act, w.r_dev, w.dPre2);
   crit_dw3_kernel<<<dim3(512 / DW3_CH, w.slabs), 256, 0, st>>>(dfeat, lddf, w.H2c, w.slot, B, w.b_per_slab, w.dw3part,
                                                                 w.db3part);
   reduce_slabs_kernel<<<pm_cdiv(512 * 256, 256), 256, 0, st>>>(w.dw3part, w.slabs, 512 * 256, g->W3);
@@ -588,8 +662,12 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
   else rc = pm_linear_backward(w.H1c, 128, p->W2, w.dPre2, 256, g->W2, g->b2, w.dPre1, 128, rmax, 256, 128, act, w.r_dev, w.lin, s);
   if (rc) return rc;
   // 5. layer 1: dW1, db1 (no dx: the cloud is an input)
-  if ((rc = pm_linear_backward(w.Xc, C, p->W1, w.dPre1, 128, g->W1, g->b1, nullptr, 0, rmax, 128, C, PM_ACT_NONE,
-                               w.r_dev, w.lin, s))) return rc;
+  if (tc) {
+    crit_dw1_kernel<<<DW1_SLABS, 256, 0, st>>>(w.dPre1, w.Xc, C, w.r_dev, w.lin);
+    crit_dw1_reduce_kernel<<<pm_cdiv(128 * (CMAX + 1), 8), 256, 0, st>>>(w.lin, DW1_SLABS, C, g->W1, g->b1);
+    PM_CHECK_LAUNCH("pm_pointnet_encode_backward/dw1");
+  } else if ((rc = pm_linear_backward(w.Xc, C, p->W1, w.dPre1, 128, g->W1, g->b1, nullptr, 0, rmax, 128, C, PM_ACT_NONE,
+                                      w.r_dev, w.lin, s))) return rc;
   return PM_OK;
 }
 
