@@ -322,10 +322,6 @@ int pm_tsdf_voxel_tables(const float* cam_pose_dev /* (M,4,4) */, int M, const f
                          const float* vol_origin, int32_t* pix_off, float* pix_z, pm_stream_t s);
 int pm_tsdf_integrate(const float* depth, int E, int M, int H, int W, const int32_t* pix_off, const float* pix_z, float size,
                       int resolution, float default_tsdf, float* out, pm_stream_t s);
-/* same contract as pm_tsdf_integrate for M <= 4 views, one gather pass (EXPERIMENTAL: not yet validated on a GPU, not used by the
- * host mirror) */
-int pm_tsdf_integrate_onepass(const float* depth, int E, int M, int H, int W, const int32_t* pix_off, const float* pix_z, float size,
-                              int resolution, float default_tsdf, float* out, pm_stream_t s);
 /* replaces utils/depth2tsdf.py:103-119 (TSDFVolume.sparse_voxel after the fusion): voxels with lo < tsdf < hi (0.2 / -0.2 there) in
  * row-major order -> K farthest points on their integer coordinates (pytorch3d semantics: start at the first, first index on
  * ties) -> out (E, K, 4) = (x, y, z, tsdf).  An env whose band is empty returns voxel 0 K times (the reference fails there). */

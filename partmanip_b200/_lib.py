@@ -75,7 +75,6 @@ SIGNATURES = {
     "pm_fps_cluster_max_active": (I, []),
     "pm_tsdf_voxel_tables": (I, [P, I, C.POINTER(F), I, I, F, I, C.POINTER(F), P, P, P]),
     "pm_tsdf_integrate": (I, [P, I, I, I, I, P, P, F, I, F, P, P]),
-    "pm_tsdf_integrate_onepass": (I, [P, I, I, I, I, P, P, F, I, F, P, P]),
     "pm_tsdf_sparse_voxel_ws_bytes": (SZ, [I, I, I]),
     "pm_tsdf_sparse_voxel": (I, [P, I, I, F, F, I, P, P, SZ, P]),
     "pm_farthest_point_sample": (I, [P, I, I, I, I, P, P, P, SZ, P]),

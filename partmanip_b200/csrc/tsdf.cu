@@ -64,42 +64,61 @@ tsdf_integrate_kernel(const float* __restrict__ depth /* (E,M,HW) */, const int3
   }
 }
 
-// One-pass variant (M <= 4 views): the per-view (tsdf, valid) pairs stay in registers, so every depth pixel and table entry is
-// gathered once instead of twice.  Same arithmetic and order as tsdf_integrate_kernel.  NOT YET RUN ON A GPU (written after the
-// round's GPU budget was spent): reachable only through pm_tsdf_integrate_onepass, which nothing calls by default.
-__global__ void __launch_bounds__(256)
-tsdf_integrate_onepass_kernel(const float* __restrict__ depth, const int32_t* __restrict__ pix_off, const float* __restrict__ pix_z,
-                              int E, int M, int HW, int R3, float trunc, float default_tsdf, float* __restrict__ out) {
-  const int64_t total = (int64_t)E * R3;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int e = (int)(i / R3), v = (int)(i - (int64_t)e * R3);
-    const float* de = depth + (int64_t)e * M * HW;
-    float t[4];
-    bool vp[4];
-    int cnt = 0;
+// M <= 4 views (the reference uses 3): one pass, blocked for gather locality.  A CTA owns a 4 x 4 bundle of z-columns (800 voxels
+// at R = 50) for a group of 8 envs: the bundle projects onto a narrow band of each view, so the 32-byte sectors its gathers touch
+// are shared by many voxels (the z-fastest grid-stride walk of the generic kernel touched about one sector per gather and did it
+// twice); the voxel -> pixel table entries are loaded once per voxel and reused for the 8 envs.  Per-view (tsdf, valid) pairs stay
+// in registers.  Same arithmetic and order as tsdf_integrate_kernel: bit-identical.  (Measured alternative: env-outer / voxel-inner
+// with the table entries of 4 voxels per thread in registers — 1.75 ms instead of 1.14 ms at E = 1024.)
+constexpr int TB_COLS = 4, TB_ENVS = 8, TB_THREADS = 256;
+__global__ void __launch_bounds__(TB_THREADS)
+tsdf_integrate_blocked_kernel(const float* __restrict__ depth, const int32_t* __restrict__ pix_off, const float* __restrict__ pix_z,
+                              int E, int M, int HW, int R, float trunc, float default_tsdf, float* __restrict__ out) {
+  const int R3 = R * R * R;
+  const int nb = (R + TB_COLS - 1) / TB_COLS;                           // column bundles per axis
+  const int bx = blockIdx.x / nb, by = blockIdx.x % nb;
+  const int e0 = blockIdx.y * TB_ENVS, e1 = min(E, e0 + TB_ENVS);
+  const int nx = min(TB_COLS, R - bx * TB_COLS), ny = min(TB_COLS, R - by * TB_COLS);
+  const int n_vox = nx * ny * R;
+  for (int idx = threadIdx.x; idx < n_vox; idx += TB_THREADS) {
+    const int col = idx / R, z = idx - col * R;
+    const int x = bx * TB_COLS + col / ny, y = by * TB_COLS + col % ny;
+    const int v = (x * R + y) * R + z;
+    int off[4];
+    float pz[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      t[m] = 0.f;
-      vp[m] = false;
-      if (m < M) {
-        const int off = __ldg(pix_off + m * R3 + v);
-        const float dv = __ldg(de + (int64_t)m * HW + (off < 0 ? 0 : off));
-        const float diff = __fsub_rn(dv, __ldg(pix_z + m * R3 + v));
-        t[m] = fminf(__fdiv_rn(diff, trunc), 1.f);
-        vp[m] = off >= 0 && dv > 0.f && diff >= -trunc;
-        cnt += vp[m] ? 1 : 0;
-      }
+      off[m] = -1; pz[m] = 0.f;
+      if (m < M) { off[m] = __ldg(pix_off + m * R3 + v); pz[m] = __ldg(pix_z + m * R3 + v); }
     }
-    const float w = __fdiv_rn(1.f, (float)cnt);
-    float acc = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      const float* de = depth + (int64_t)e * M * HW;
+      float t[4];
+      bool vp[4];
+      int cnt = 0;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m < M) {
-        const float prod = __fmul_rn(t[m], vp[m] ? w : 0.f);
-        acc = m == 0 ? prod : __fadd_rn(acc, prod);
+      for (int m = 0; m < 4; ++m) {
+        t[m] = 0.f;
+        vp[m] = false;
+        if (m < M) {
+          const float dv = __ldg(de + (int64_t)m * HW + (off[m] < 0 ? 0 : off[m]));     // invalid pixels read pixel (0,0), as the reference
+          const float diff = __fsub_rn(dv, pz[m]);
+          t[m] = fminf(__fdiv_rn(diff, trunc), 1.f);
+          vp[m] = off[m] >= 0 && dv > 0.f && diff >= -trunc;
+          cnt += vp[m] ? 1 : 0;
+        }
       }
+      const float w = __fdiv_rn(1.f, (float)cnt);
+      float acc = 0.f;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (m < M) {
+          const float prod = __fmul_rn(t[m], vp[m] ? w : 0.f);
+          acc = m == 0 ? prod : __fadd_rn(acc, prod);
+        }
+      }
+      out[(int64_t)e * R3 + v] = __fadd_rn(acc, cnt == 0 ? default_tsdf : 0.f);
     }
-    out[i] = __fadd_rn(acc, cnt == 0 ? default_tsdf : 0.f);
   }
 }
 
@@ -130,23 +149,16 @@ int pm_tsdf_integrate(const float* depth, int E, int M, int H, int W, const int3
   const int R3 = resolution * resolution * resolution;
   const int64_t total = (int64_t)E * R3;
   const float trunc = (float)(4.0 * ((double)size / resolution));                    // depth2tsdf.py:16-17
-  const int blocks = (int)((total + 255) / 256 < (int64_t)PM_NUM_SMS * 16 ? (total + 255) / 256 : (int64_t)PM_NUM_SMS * 16);
-  tsdf_integrate_kernel<<<blocks, 256, 0, pm_st(s)>>>(depth, pix_off, pix_z, E, M, H * W, R3, trunc, default_tsdf, out);
+  if (M <= 4) {
+    const int nb = pm_cdiv(resolution, TB_COLS);
+    PM_REQUIRE(pm_cdiv(E, TB_ENVS) <= 65535, PM_ERR_SHAPE, "pm_tsdf_integrate: E=%d too large for one launch", E);
+    tsdf_integrate_blocked_kernel<<<dim3(nb * nb, pm_cdiv(E, TB_ENVS)), TB_THREADS, 0, pm_st(s)>>>(depth, pix_off, pix_z, E, M, H * W,
+                                                                                                  resolution, trunc, default_tsdf, out);
+  } else {
+    const int blocks = (int)((total + 255) / 256 < (int64_t)PM_NUM_SMS * 16 ? (total + 255) / 256 : (int64_t)PM_NUM_SMS * 16);
+    tsdf_integrate_kernel<<<blocks, 256, 0, pm_st(s)>>>(depth, pix_off, pix_z, E, M, H * W, R3, trunc, default_tsdf, out);
+  }
   PM_CHECK_LAUNCH("pm_tsdf_integrate");
-  return PM_OK;
-}
-
-int pm_tsdf_integrate_onepass(const float* depth, int E, int M, int H, int W, const int32_t* pix_off, const float* pix_z, float size,
-                              int resolution, float default_tsdf, float* out, pm_stream_t s) {
-  PM_REQUIRE(depth && pix_off && pix_z && out, PM_ERR_ARG, "pm_tsdf_integrate_onepass: null pointer");
-  PM_REQUIRE(E > 0 && M > 0 && M <= 4 && H > 0 && W > 0 && resolution > 0 && resolution <= 512 && size > 0.f, PM_ERR_SHAPE,
-             "pm_tsdf_integrate_onepass: E=%d M=%d (<= 4) H=%d W=%d resolution=%d", E, M, H, W, resolution);
-  const int R3 = resolution * resolution * resolution;
-  const int64_t total = (int64_t)E * R3;
-  const float trunc = (float)(4.0 * ((double)size / resolution));
-  const int blocks = (int)((total + 255) / 256 < (int64_t)PM_NUM_SMS * 16 ? (total + 255) / 256 : (int64_t)PM_NUM_SMS * 16);
-  tsdf_integrate_onepass_kernel<<<blocks, 256, 0, pm_st(s)>>>(depth, pix_off, pix_z, E, M, H * W, R3, trunc, default_tsdf, out);
-  PM_CHECK_LAUNCH("pm_tsdf_integrate_onepass");
   return PM_OK;
 }
 

@@ -487,17 +487,16 @@ def tsdf_voxel_tables(cam_pose: Tensor, cam_intr, im_h: int, im_w: int, size: fl
 
 
 def tsdf_integrate(depth: Tensor, pix_off: Tensor, pix_z: Tensor, size: float, resolution: int, default_tsdf: float = 1.0,
-                   out: Optional[Tensor] = None, onepass: bool = False) -> Tensor:
-    """utils/depth2tsdf.py:68-86: depth (E,M,H,W) fp32 -> fused TSDF volume (E, R, R, R).  onepass=True selects the experimental
-    single-gather kernel (M <= 4; not yet validated on a GPU — nothing passes it by default)."""
+                   out: Optional[Tensor] = None) -> Tensor:
+    """utils/depth2tsdf.py:68-86: depth (E,M,H,W) fp32 -> fused TSDF volume (E, R, R, R)."""
     E, M, H, W = depth.shape
     R = int(resolution)
     assert _f32(depth, "depth").is_contiguous() and pix_off.dtype == torch.int32 and pix_off.shape == (M, R ** 3) and pix_off.is_contiguous()
     assert _f32(pix_z, "pix_z").is_contiguous() and pix_z.shape == (M, R ** 3)
     if out is None:
         out = torch.empty(E, R, R, R, device=depth.device, dtype=torch.float32)
-    fn, name = (lib.pm_tsdf_integrate_onepass, "pm_tsdf_integrate_onepass") if onepass else (lib.pm_tsdf_integrate, "pm_tsdf_integrate")
-    check(fn(_p(depth), E, M, H, W, _p(pix_off), _p(pix_z), float(size), R, float(default_tsdf), _p(out), _stream()), name)
+    check(lib.pm_tsdf_integrate(_p(depth), E, M, H, W, _p(pix_off), _p(pix_z), float(size), R, float(default_tsdf), _p(out), _stream()),
+          "pm_tsdf_integrate")
     return out
 
 
