@@ -278,6 +278,19 @@ int pm_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
                  int64_t n_clip, float max_norm /* <=0: no clipping */, float beta1, float beta2,
                  float eps, float* opt_state, const int32_t* skip_flag, void* ws, pm_stream_t s);
 
+/* K7f  ONE launch per optimiser step: cross-GPU gradient all-reduce (one-shot pull over NVLink peer memory) + KL-skip decision
+ * (pm_ppo_actor_finalize's arithmetic, ppo.py:335-338) + clip + Adam (pm_adam_step's arithmetic).  grad_local: this rank's
+ * gradients followed by n_tail extra floats that are summed over ranks too (finalize != 0: tail[0] = sum surrogate, tail[1] = sum
+ * KL).  world > 1: grad_peers_dev / flag_peers_dev are DEVICE arrays of `world` pointers to every rank's gradient buffer /
+ * 64-word flag buffer (symmetric memory mapped into this process; entry `rank` is the local one), flags_local = this rank's flag
+ * buffer, zero before the first call; every rank must call in lockstep.  The workspace (pm_fused_step_ws_bytes) must be ZEROED
+ * before the first call and then belong to this optimiser only (it carries the launch sequence number). */
+size_t pm_fused_step_ws_bytes(int64_t n, int n_tail);
+int pm_fused_step(float* params, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t n_clip, int n_tail, float max_norm, float beta1,
+                  float beta2, float eps, float* opt_state, const float* grad_local, const float* const* grad_peers_dev,
+                  uint32_t* const* flag_peers_dev, uint32_t* flags_local, int rank, int world, int finalize, float inv_batch,
+                  float desired_kl, float* acc, int32_t* skip_flag, void* ws, pm_stream_t s);
+
 /* ------------------------------------------------------------------------------------------
  * K8  rollout-buffer helpers (storage.py:43-56 is cudaMemcpyAsync; the random sampler needs gathers)
  * ------------------------------------------------------------------------------------------ */

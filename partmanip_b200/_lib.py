@@ -69,6 +69,8 @@ SIGNATURES = {
     "pm_pointnet_bwd_tc_last_error": (I, [P, P]),
     "pm_adam_ws_bytes": (SZ, [L]),
     "pm_adam_step": (I, [P, P, P, P, L, L, F, F, F, F, P, P, P, P]),
+    "pm_fused_step_ws_bytes": (SZ, [L, I]),
+    "pm_fused_step": (I, [P, P, P, L, L, I, F, F, F, F, P, P, P, P, P, I, I, I, F, F, P, P, P, P]),
     "pm_depth2pc_backproject": (I, [P, I, I, I, I, C.POINTER(F), P, C.POINTER(F), F, P, P]),
     "pm_depth2pc_backproject_views": (I, [P, I, I, I, I, I, I, F, C.POINTER(F), P, C.POINTER(F), F, P, P]),
     "pm_fps_ws_bytes": (SZ, [I, I]),
@@ -113,7 +115,7 @@ KERNELS_PER_CALL = {
     "pm_policy_logprob": 1, "pm_ppo_actor_loss": 2, "pm_ppo_actor_finalize": 1, "pm_value_loss": 2, "pm_abs_sum": 2,
     "pm_accumulate": 1, "pm_dagger_loss": 2, "pm_linear_forward": 1, "pm_linear_backward": 4, "pm_linear_forward_tc": 1, "pm_linear_backward_tc": 5, "pm_pointnet_center": 1,
     "pm_pointnet_encode_forward": 2, "pm_pointnet_encode_backward": 3, "pm_pointnet_head_forward": 1,
-    "pm_pointnet_head_backward": 3, "pm_adam_step": 3, "pm_gather_rows": 1,
+    "pm_pointnet_head_backward": 3, "pm_adam_step": 3, "pm_fused_step": 1, "pm_gather_rows": 1,
     "pm_copy_rows": 1,
 }
 LAUNCHES = [0]

@@ -42,15 +42,23 @@ class FlatAdam:
     pm_adam_step.  state_dict()/load_state_dict() speak torch.optim's format so reference checkpoints round-trip
     (ppo.py:89-90, 121-122)."""
 
-    def __init__(self, flat, params, offsets, group_sizes, lr, n_clip, max_norm, index_offset=0, n_unstepped_tail=0):
+    def __init__(self, flat, params, offsets, group_sizes, lr, n_clip, max_norm, index_offset=0, n_unstepped_tail=0, fused=False):
         """`index_offset` / `n_unstepped_tail`: parameters of the reference optimiser that sit before / after this buffer's
         tensors in `module.parameters()` order and never receive a gradient (DAgger: log_std before, the critic after —
         dagger.py:56); they shift the state indices and widen param_groups[0]['params'] so the dict is torch.optim.Adam's."""
         self.flat, self.params, self.offsets, self.group_sizes = flat, params, offsets, group_sizes
         self.index_offset, self.n_unstepped_tail = int(index_offset), int(n_unstepped_tail)
         # gradient buffer with a 4-float tail: per-step scalars that must be summed over ranks (sum surrogate, sum KL) ride
-        # in the SAME all-reduce as the gradients (one collective per optimiser step)
-        self.grad_ext = torch.zeros(flat.numel() + 4, device=flat.device, dtype=torch.float32)
+        # in the SAME reduction as the gradients.  Multi-rank on NCCL: the buffer lives in symmetric memory so that the fused
+        # step kernel (csrc/fused_step.cu) can pull the peers' gradients over NVLink itself — one launch per optimiser step
+        # instead of all-reduce + finalize + 3 Adam launches; without symmetric memory the NCCL all-reduce path remains.
+        self.sym = parallel.SymmetricGrad.create(flat.numel() + 4, flat.device) if (fused and flat.is_cuda) else None
+        self.fused = bool(fused and flat.is_cuda and (parallel.world() == 1 or self.sym is not None))
+        if self.sym is not None:
+            self.grad_ext = self.sym.buf
+        else:
+            self.grad_ext = torch.zeros(flat.numel() + 4, device=flat.device, dtype=torch.float32)
+        self._fused_ws = ops.fused_step_workspace(flat.numel(), 4, flat.device) if self.fused else None
         self.grad = self.grad_ext[:flat.numel()]
         self.tail = self.grad_ext[flat.numel():]
         self.exp_avg = torch.zeros_like(flat)
@@ -71,6 +79,11 @@ class FlatAdam:
     def step(self, skip_flag=None):
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.n_clip, self.max_norm, self.opt_state,
                       skip_flag)
+
+    def step_fused(self, finalize=None):
+        """[all-reduce over ranks] + [KL-skip decision: finalize = (inv_batch, desired_kl, acc, skip_flag)] + clip + Adam, one launch."""
+        ops.fused_step(self.flat, self.grad_ext, self.exp_avg, self.exp_avg_sq, self.n_clip, 4, self.max_norm, self.opt_state,
+                       self._fused_ws, peers=self.sym.peers() if self.sym is not None else None, finalize=finalize)
 
     @property
     def step_count(self) -> int:
@@ -173,11 +186,12 @@ class ppo:
         self.storage = RolloutStorage(self.num_envs, self.n_steps, self.num_obs, self.num_actions, self.device,
                                       self.default_succ_value, self.tricks['whole_adv_norm'], cfg['sampler'])
         a_params = list(ac.actor.parameters())
+        fused = bool(cfg.get('fused_step', True))        # build extension: one kernel per optimiser step (A/B switch)
         self.optimizer_actor = FlatAdam(ac.actor_flat, a_params + [ac.log_std], ac.actor_offs, [len(a_params), 1], self.lr,
-                                        ac.actor_n_clip, self.max_grad_norm)
+                                        ac.actor_n_clip, self.max_grad_norm, fused=fused)
         c_params = list(ac.critic.parameters())
         self.optimizer_critic = FlatAdam(ac.critic_flat, c_params, ac.critic_offs, [len(c_params)], self.lr,
-                                         ac.critic_flat.numel(), self.max_grad_norm)
+                                         ac.critic_flat.numel(), self.max_grad_norm, fused=fused)
         self._actor_grads = ac.grad_views(self.optimizer_actor.grad, "actor")
         self._critic_grads = ac.grad_views(self.optimizer_critic.grad, "critic")
         # device-side bookkeeping for one update(): acc = [sum surrogate, sum kl, count, kl_max, sum value loss]
@@ -435,9 +449,12 @@ class ppo:
                                    mb['adv'].reshape(-1), adv_stats, inv_b, self.epsilon_clip, ac.max_action, squash,
                                    self._stats_a, dmu, self._actor_grads[-1])
                 ac.actor.runner.backward(mb['obs'], dmu, self._actor_grads[:-1])
-                parallel.all_reduce_sum_(self.optimizer_actor.grad_ext)   # gradients + [sum surrogate, sum KL] in one collective
-                ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)   # rank-consistent KL-skip
-                self.optimizer_actor.step(self._skip)
+                if self.optimizer_actor.fused:     # all-reduce + rank-consistent KL-skip + clip + Adam: ONE launch
+                    self.optimizer_actor.step_fused((inv_b, self.desired_kl, self._acc, self._skip))
+                else:
+                    parallel.all_reduce_sum_(self.optimizer_actor.grad_ext)   # gradients + [sum surrogate, sum KL] in one collective
+                    ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)   # rank-consistent KL-skip
+                    self.optimizer_actor.step(self._skip)
         # ---- phase 2: critic (ppo.py:359-384)
         n_critic = 0
         for epoch in range(self.n_updates):
@@ -456,8 +473,11 @@ class ppo:
                 ops.value_loss(v, mb['ret'].reshape(-1), mb['val'].reshape(-1), clip_delta, inv_b, self._stats_v, dv)
                 ops.accumulate(self._stats_v, inv_b, self._acc, 4)
                 ac.critic.runner.backward(mb['obs'], dv, self._critic_grads)
-                parallel.all_reduce_sum_(self.optimizer_critic.grad)
-                self.optimizer_critic.step(None)
+                if self.optimizer_critic.fused:
+                    self.optimizer_critic.step_fused(None)
+                else:
+                    parallel.all_reduce_sum_(self.optimizer_critic.grad)
+                    self.optimizer_critic.step(None)
                 n_critic += 1
         parallel.all_reduce_sum_(self._acc[4:5])
         self._n_critic = n_critic

@@ -440,6 +440,28 @@ def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor
           "pm_adam_step")
 
 
+def fused_step_workspace(n: int, n_tail: int, device) -> Tensor:
+    """Zeroed, optimiser-private workspace of pm_fused_step (it carries the launch sequence number and the grid-barrier counter)."""
+    return torch.zeros(int(lib.pm_fused_step_ws_bytes(int(n), int(n_tail))), dtype=torch.uint8, device=device)
+
+
+def fused_step(params: Tensor, grad_ext: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, n_clip: int, n_tail: int, max_norm: float,
+               opt_state: Tensor, ws: Tensor, *, peers=None, finalize=None, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8):
+    """One launch: [all-reduce over `peers`] + [KL-skip] + clip + Adam.  grad_ext: (n + n_tail,) this rank's gradients + tail.
+    peers = (grad_ptrs_dev, flag_ptrs_dev, flags_local_tensor, rank, world) from parallel.SymmetricGrad, or None (one process).
+    finalize = (inv_batch, desired_kl, acc, skip_flag) for the actor, None for the critic."""
+    n = params.numel()
+    for t in (params, exp_avg, exp_avg_sq):
+        _f32(t, "adam buffer")
+        assert t.is_contiguous() and t.numel() == n
+    assert _f32(grad_ext, "grad_ext").is_contiguous() and grad_ext.numel() == n + n_tail
+    gp, fp, fl, rank, world = peers if peers is not None else (None, None, None, 0, 1)
+    inv_b, dkl, acc, skip = finalize if finalize is not None else (0.0, 0.0, None, None)
+    check(lib.pm_fused_step(_p(params), _p(exp_avg), _p(exp_avg_sq), n, int(n_clip), int(n_tail), float(max_norm), float(beta1),
+                            float(beta2), float(eps), _p(opt_state), _p(grad_ext), gp, fp, _p(fl), int(rank), int(world),
+                            int(finalize is not None), float(inv_b), float(dkl), _p(acc), _p(skip), _p(ws), _stream()), "pm_fused_step")
+
+
 # ------------------------------------------------------------------------------------------- K8 storage
 def gather_rows(src: Tensor, idx: Tensor, out: Tensor) -> Tensor:
     assert idx.dtype == torch.int64 and idx.is_contiguous() and idx.is_cuda

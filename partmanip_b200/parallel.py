@@ -44,3 +44,39 @@ def inv_global_batch(local_batch: int) -> float:
 def global_count(local_rows: int) -> float:
     """Rows behind an all-reduced column sum (RMS.py:14 `x.mean(dim=0)` over the GLOBAL env batch)."""
     return float(local_rows * world())
+
+
+class SymmetricGrad:
+    """A gradient buffer every rank can read with plain loads (NVLink peer memory), for the fused all-reduce + clip + Adam kernel
+    (csrc/fused_step.cu).  Built on torch.distributed._symmetric_memory: the same allocation is mapped into every rank's
+    address space; `grad_ptrs` / `flag_ptrs` are DEVICE arrays of the `world` peer pointers.  `create()` returns None when the
+    process group cannot provide it (one process, gloo, no P2P): the caller then keeps the NCCL all-reduce path."""
+
+    def __init__(self, buf, flags, hdl, fhdl):
+        self.buf, self.flags, self._hdl, self._fhdl = buf, flags, hdl, fhdl
+        self.grad_ptrs, self.flag_ptrs = int(hdl.buffer_ptrs_dev), int(fhdl.buffer_ptrs_dev)
+        self.rank, self.world = int(hdl.rank), int(hdl.world_size)
+
+    @staticmethod
+    def create(numel: int, device):
+        if world() == 1 or dist.get_backend() != "nccl" or not str(device).startswith("cuda"):
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = dist.group.WORLD
+            if hasattr(symm, "enable_symm_mem_for_group") and not symm.is_symm_mem_enabled_for_group(group.group_name):
+                symm.enable_symm_mem_for_group(group.group_name)
+            buf = symm.empty(int(numel), dtype=torch.float32, device=device)
+            flags = symm.empty(64, dtype=torch.int32, device=device)
+            buf.zero_()
+            flags.zero_()
+            hdl, fhdl = symm.rendezvous(buf, group), symm.rendezvous(flags, group)
+            torch.cuda.synchronize()
+            dist.barrier()                      # every rank's flags are zero before anybody's first fused step
+            return SymmetricGrad(buf, flags, hdl, fhdl)
+        except Exception as e:  # pragma: no cover - depends on the platform
+            print(f"[partmanip_b200] symmetric memory unavailable ({type(e).__name__}: {e}); gradients go through NCCL all-reduce")
+            return None
+
+    def peers(self):
+        return (self.grad_ptrs, self.flag_ptrs, self.flags, self.rank, self.world)

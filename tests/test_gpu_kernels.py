@@ -204,6 +204,36 @@ def test_adam_clip_matches_torch_optimizer(ops):
     assert float(st[0]) == 5.0
 
 
+@pytest.mark.parametrize("n,n_clip", [(1010, 1000), (470197, 470187), (7, 7), (4096, 0)])
+def test_fused_step_equals_finalize_plus_adam(ops, n, n_clip):
+    """K7f at world == 1: one launch == pm_ppo_actor_finalize + pm_adam_step on the same inputs (weights, moments, step counter, the
+    KL-skip flag and the loss / KL accumulators), including a skipped minibatch (ppo.py:337-338) and the critic form (no
+    finalize).  The norm's fp64 partial sums are grouped differently, so weights agree to an ulp rather than bit for bit."""
+    torch.manual_seed(n)
+    p0 = torch.randn(n)
+    mk = lambda: (cu(p0), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.tensor([0, 5e-5, 0, 0, 0, 0, 0, 0], device=DEV))
+    pa, ma, va, sa = mk()
+    pb, mb, vb, sb = mk()
+    acc_a, acc_b = torch.zeros(8, device=DEV), torch.zeros(8, device=DEV)
+    skip_a, skip_b = torch.zeros(1, device=DEV, dtype=torch.int32), torch.zeros(1, device=DEV, dtype=torch.int32)
+    ws = ops.fused_step_workspace(n, 4, DEV)
+    B, desired_kl = 64, 0.02
+    for step in range(5):
+        gext = torch.cat([torch.randn(n) * (3.0 if step % 2 else 0.01), torch.tensor([-12.5 * (step + 1), 0.3 * B if step == 2 else 0.004 * B, 0.0, 0.0])])
+        ga, gb = cu(gext), cu(gext)
+        finalize = step != 4                                      # the last step in the critic form
+        if finalize:
+            ops.ppo_actor_finalize(ga[n:], 1.0 / B, desired_kl, acc_a, skip_a)
+        ops.adam_step(pa, ga[:n], ma, va, n_clip, 0.5, sa, skip_a if finalize else None)
+        ops.fused_step(pb, gb, mb, vb, n_clip, 4, 0.5, sb, ws, finalize=(1.0 / B, desired_kl, acc_b, skip_b) if finalize else None)
+        assert int(skip_a) == int(skip_b) == (1 if step == 2 else 0) or not finalize
+        assert float(sa[0]) == float(sb[0]) and torch.equal(acc_a, acc_b)
+        assert math.isclose(float(sa[2]), float(sb[2]), rel_tol=1e-6, abs_tol=1e-30)
+        assert float((pa - pb).abs().max()) <= 1e-7 and float((ma - mb).abs().max()) <= 1e-7 * float(ma.abs().max() + 1e-30)
+        assert float((va - vb).abs().max()) <= 1e-6 * float(va.abs().max() + 1e-30)
+    assert float(sb[0]) == 4.0 and float(acc_b[2]) == 3.0
+
+
 # ------------------------------------------------------------------------------------------------ K3
 @pytest.mark.parametrize("name,act", [("mlp_actor.npz", "tanh"), ("mlp_critic.npz", "elu")])
 def test_mlp_golden_forward_backward(ops, name, act):
