@@ -342,6 +342,24 @@ size_t pm_tsdf_sparse_voxel_ws_bytes(int E, int resolution, int K);
 int pm_tsdf_sparse_voxel(const float* tsdf /* (E,R,R,R) */, int E, int resolution, float lo, float hi, int K, float* out, void* ws,
                          size_t ws_bytes, pm_stream_t s);
 
+/* ------------------------------------------------------------------------------------------
+ * NEXT ROW (second half): the Conv3D student on the fused TSDF volume — algorithms/algo_utils/network.py:56-63
+ * (conv_stride = nn.Conv3d(stride, padding = k // 2)), :67-97 (Conv3DNet), :119-135 (Encoder).  A convolution = pm_conv3d_im2col
+ * + pm_linear_forward_tc (bias + activation fused) on CHANNELS-LAST activations ((sample, voxel) rows x channels); its backward =
+ * pm_linear_backward_tc + pm_conv3d_col2im.  The patch column order (c, kd, kh, kw) is nn.Conv3d's weight.view(Cout, -1) order.
+ * ------------------------------------------------------------------------------------------ */
+int pm_conv3d_out_dim(int Din, int k, int s);
+/* cols[(b, od, oh, ow), (c, kd, kh, kw)] = in[b*sample_stride + voxel*ld_in + c] (0 outside the volume); row stride Kpad >= C*k^3,
+ * padding columns zeroed.  in: voxel (id, ih, iw) of sample b at in + b*sample_stride + ((id*Din + ih)*Din + iw)*ld_in. */
+int pm_conv3d_im2col(const float* in, int64_t ld_in, int64_t sample_stride, int B, int C, int Din, int k, int s, float* cols, int Kpad,
+                     pm_stream_t st);
+/* adjoint of im2col in gather form (deterministic), times act'(y): din[(b, voxel), c] = (sum of covering patch entries) * act'(y[...]) */
+int pm_conv3d_col2im(const float* dcols, int Kpad, int B, int C, int Din, int k, int s, const float* y, int act, float* din,
+                     pm_stream_t st);
+/* to_rows != 0: out[b*ld_row + c*P + pos] = in[(b*P + pos)*C + c] (channels-last -> x.reshape(batch, -1) order, network.py:92-96);
+ * to_rows == 0: out[(b*P + pos)*C + c] = in[b*ld_row + c*P + pos] */
+int pm_conv3d_flatten(const float* in, float* out, int B, int P, int C, int64_t ld_row, int to_rows, pm_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,10 @@ SIGNATURES = {
     "pm_tsdf_sparse_voxel_ws_bytes": (SZ, [I, I, I]),
     "pm_tsdf_sparse_voxel": (I, [P, I, I, F, F, I, P, P, SZ, P]),
     "pm_farthest_point_sample": (I, [P, I, I, I, I, P, P, P, SZ, P]),
+    "pm_conv3d_out_dim": (I, [I, I, I]),
+    "pm_conv3d_im2col": (I, [P, L, L, I, I, I, I, I, P, I, P]),
+    "pm_conv3d_col2im": (I, [P, I, I, I, I, I, I, P, I, P, P]),
+    "pm_conv3d_flatten": (I, [P, P, I, I, I, L, I, P]),
     "pm_gather_rows": (I, [P, L, P, P, L, L, I, P]),
     "pm_copy_rows": (I, [P, L, P, L, L, I, P]),
 }

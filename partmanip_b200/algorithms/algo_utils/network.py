@@ -245,6 +245,109 @@ class PointNet(nn.Module):
         return _NetFunction.apply(self, x, *self.parameters())
 
 
+class _Conv3DRunner(_Runner):
+    """Conv3DNet on the kernels: per convolution pm_conv3d_im2col + a dense layer on tcgen05 (channels-last activations), the head as
+    two dense layers; backward = the dense backward + pm_conv3d_col2im."""
+    SPECS = ((1, 16, 5, 3), (16, 32, 3, 3), (32, 32, 3, 2))          # (Cin, Cout, k, stride): network.py:70
+
+    def _get(self, B: int, dev):
+        b = self._bufs.get(B)
+        if b is None or b["dev"] != dev:
+            net = self.net
+            dims = [net.res]
+            for _, _, k, s in self.SPECS:
+                dims.append(ops.conv3d_out_dim(dims[-1], k, s))
+            b = {"dev": dev, "dims": dims, "cols": [], "y": [], "dcols": [], "dpre": []}
+            for i, (ci, co, k, s) in enumerate(self.SPECS):
+                rows, kpad = B * dims[i + 1] ** 3, (ci * k ** 3 + 3) // 4 * 4
+                b["cols"].append(torch.empty(rows, kpad, device=dev))
+                b["y"].append(torch.empty(rows, co, device=dev))
+                b["dcols"].append(torch.empty(rows, kpad, device=dev) if i > 0 else None)
+                b["dpre"].append(torch.empty(rows, co, device=dev))
+            F = net.feat_dim
+            b.update(flat=torch.empty(B, F, device=dev), h=torch.empty(B, 256, device=dev), out=torch.empty(B, net.output_dim, device=dev),
+                     dh=torch.empty(B, 256, device=dev), dflat=torch.empty(B, F, device=dev))
+            self._bufs[B] = b
+        return b
+
+    def _convs(self):
+        e = self.net.encoder
+        return [e.conv1, e.conv2, e.conv3]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        net, prec = self.net, self.net.precision
+        B = x.shape[0]
+        buf = self._get(B, x.device)
+        dims, act = buf["dims"], net.act_name
+        src, ld_in, sstride = x, 1, x.stride(0)                      # the TSDF volume: one channel, voxels contiguous per sample
+        for i, ((ci, co, k, s), conv) in enumerate(zip(self.SPECS, self._convs())):
+            ops.conv3d_im2col(src, ld_in, sstride, B, ci, dims[i], k, s, buf["cols"][i])
+            ops.linear_forward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), conv.bias, act, prec, out=buf["y"][i])
+            src, ld_in, sstride = buf["y"][i], co, dims[i + 1] ** 3 * co
+        P = dims[3] ** 3
+        ops.conv3d_flatten(buf["y"][2], buf["flat"], B, P, 32, net.feat_dim, True)
+        if net.proprio_shape:
+            ops.copy_rows(x[:, x.shape[1] - net.proprio_shape:], buf["flat"][:, 32 * P:])
+        f = net.final_mlp
+        ops.linear_forward_tc(buf["flat"], f[0].weight, f[0].bias, act, prec, out=buf["h"])
+        return ops.linear_forward_tc(buf["h"], f[2].weight, f[2].bias, None, prec, out=buf["out"])
+
+    def backward(self, x: torch.Tensor, dout: torch.Tensor, grads: List[torch.Tensor]):
+        """grads in parameter order: encoder.conv{1,2,3}.{weight,bias}, final_mlp.{0,2}.{weight,bias}; uses the last forward(x)."""
+        net, prec = self.net, self.net.precision
+        B = x.shape[0]
+        buf = self._get(B, x.device)
+        dims, act = buf["dims"], net.act_name
+        f = net.final_mlp
+        P = dims[3] ** 3
+        ops.linear_backward_tc(buf["h"], f[2].weight, dout, grads[8], grads[9], buf["dh"], act, prec)
+        # d flat = (dh W0) * act'(flat): on the encoder columns flat IS act(conv3 pre-activation), so this is dPre3 (flatten order)
+        ops.linear_backward_tc(buf["flat"], f[0].weight, buf["dh"], grads[6], grads[7], buf["dflat"], act, prec)
+        ops.conv3d_flatten(buf["dflat"], buf["dpre"][2], B, P, 32, net.feat_dim, False)
+        for i in (2, 1, 0):
+            ci, co, k, s = self.SPECS[i]
+            conv = self._convs()[i]
+            ops.linear_backward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), buf["dpre"][i], grads[2 * i].view(co, -1),
+                                   grads[2 * i + 1], buf["dcols"][i][:, :ci * k ** 3] if i > 0 else None, None, prec)
+            if i > 0:
+                ops.conv3d_col2im(buf["dcols"][i], B, ci, dims[i], k, s, buf["y"][i - 1], act, buf["dpre"][i - 1])
+
+
+class _Conv3DEncoder(nn.Module):
+    """network.py:119-135 `Encoder` — parameter container (conv1..conv3 as nn.Conv3d so names, shapes and default init match)."""
+
+    def __init__(self, in_channels, filters, kernels, stride):
+        super().__init__()
+        self.conv1 = nn.Conv3d(in_channels, filters[0], kernels[0], stride=stride[0], padding=kernels[0] // 2)
+        self.conv2 = nn.Conv3d(filters[0], filters[1], kernels[1], stride=stride[1], padding=kernels[1] // 2)
+        self.conv3 = nn.Conv3d(filters[1], filters[2], kernels[2], stride=stride[2], padding=kernels[2] // 2)
+
+
+class Conv3DNet(nn.Module):
+    """network.py:67-97 — the TSDF student of dagger_tsdf.yaml / bc.yaml: Encoder(1, [16,32,32], [5,3,3], [3,3,2]) on the
+    (res, res, res) volume, flatten (32*27) [cat proprio], Linear(.,256)-act-Linear(256,out).  Same constructor, parameter names
+    (`encoder.conv{1,2,3}`, `final_mlp.{0,2}`) and init order as the reference.  `net_cfg['precision']`: "fp32" (default,
+    three-term bf16 split on tcgen05, 1e-4 gate) or "bf16"."""
+
+    def __init__(self, input_dim, output_dim, net_cfg, proprio_shape):
+        super().__init__()
+        self.res = round(input_dim ** (1 / 3))
+        self.encoder = _Conv3DEncoder(1, [16, 32, 32], [5, 3, 3], [3, 3, 2])
+        self.activation = get_activation(net_cfg['activation'])
+        self.final_mlp = nn.Sequential(nn.Linear(32 * 27 + proprio_shape, 256), self.activation, nn.Linear(256, output_dim))
+        self.proprio_shape = proprio_shape
+        self.act_name = net_cfg['activation']
+        self.output_dim = output_dim
+        self.feat_dim = 32 * 27 + proprio_shape
+        self.precision = net_cfg.get('precision', 'fp32')
+        if self.precision not in ("fp32", "bf16"):
+            raise NotImplementedError(f"precision {self.precision!r}")
+        self.runner = _Conv3DRunner(self)
+
+    def forward(self, x):
+        return _NetFunction.apply(self, x, *self.parameters())
+
+
 class _NetFunction(torch.autograd.Function):
     """Autograd bridge: forward/backward through the kernels; gradients w.r.t. the parameters only
     (the observation is an input — the reference never differentiates through it either)."""

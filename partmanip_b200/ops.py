@@ -480,6 +480,31 @@ def copy_rows(src: Tensor, dst: Tensor) -> Tensor:
     return dst
 
 
+# ------------------------------------------------------------------------------------------- next row: Conv3D student
+def conv3d_out_dim(Din: int, k: int, s: int) -> int:
+    return int(lib.pm_conv3d_out_dim(int(Din), int(k), int(s)))
+
+
+def conv3d_im2col(src: Tensor, ld_in: int, sample_stride: int, B: int, C: int, Din: int, k: int, s: int, cols: Tensor):
+    """network.py:56-63 patches: src holds voxel (d,h,w) of sample b at b*sample_stride + ((d*Din+h)*Din+w)*ld_in + c."""
+    assert _f32(src, "src").is_cuda and _f32(cols, "cols").is_contiguous() and cols.dim() == 2
+    check(lib.pm_conv3d_im2col(_p(src), int(ld_in), int(sample_stride), B, C, Din, k, s, _p(cols), cols.shape[1], _stream()),
+          "pm_conv3d_im2col")
+    return cols
+
+
+def conv3d_col2im(dcols: Tensor, B: int, C: int, Din: int, k: int, s: int, y: Tensor, act, din: Tensor):
+    assert _f32(dcols, "dcols").is_contiguous() and _f32(y, "y").is_contiguous() and _f32(din, "din").is_contiguous()
+    check(lib.pm_conv3d_col2im(_p(dcols), dcols.shape[1], B, C, Din, k, s, _p(y), PM_ACT[act], _p(din), _stream()), "pm_conv3d_col2im")
+    return din
+
+
+def conv3d_flatten(src: Tensor, dst: Tensor, B: int, P: int, C: int, ld_row: int, to_rows: bool):
+    check(lib.pm_conv3d_flatten(_p(_f32(src, "src")), _p(_f32(dst, "dst")), B, P, C, int(ld_row), int(bool(to_rows)), _stream()),
+          "pm_conv3d_flatten")
+    return dst
+
+
 # ------------------------------------------------------------------------------------------- next row: depth -> point cloud
 def depth2pc_backproject(depth: Tensor, cam_intr, cam_pose: Tensor, vol_origin, size: float, out: Optional[Tensor] = None) -> Tensor:
     """utils/depth2tsdf.py:146-159.  depth (E,M,H,W) fp32 CUDA, cam_pose (M,4,4) fp32 CUDA -> masked world cloud (E, M*H*W, 3)."""

@@ -64,7 +64,9 @@ for (name, net, D, A, E), (eps_all, init_sd, ref_sd, ref_log) in zip(cases, refs
     lo = {k: (float(log[k]), float(ref_log[k])) for k in ("Train/surrogate_loss", "Train/value_function_loss", "Train/kl", "Train/kl_update_count")}
     # fraction of the 40*lr Adam displacement; the 40-step trajectory is chaotic in the max-pool argmax (see
     # tests/test_gpu_pointnet_ppo.py), so the weights get a loose gate and the logged losses/KL the tight one
-    tol = 0.1 if "bf16" not in name else 1.0
+    # (fp32 = the split-operand tensor-core kernels since round 2: single-step gradients agree to 1e-5 instead of 1e-7, so the
+    # chaotic 40-step trajectories separate a little more: measured 0.135 at world 2)
+    tol = 0.25 if "bf16" not in name else 1.0
     ok = same and worst <= tol and all(abs(a - b) <= 1e-3 * max(1.0, abs(b)) + (1e-2 if "bf16" in name else 0) for a, b in lo.values())
     bad += 0 if ok else 1
     if rank == 0:
