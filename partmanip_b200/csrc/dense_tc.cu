@@ -128,7 +128,7 @@ gemm_tc_kernel(const GemmTcP p) {
   using Plan = SmemPlan<PARTS>;
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;      // M tiles on grid.x (up to 2^31-1; a conv layer has 10^7 patch rows)
   int M = p.M, K = p.K;
   int k_begin = 0, k_end = K;
   if (EPI == EPI_DW) {
@@ -349,7 +349,7 @@ int pm_linear_forward_tc(const float* x, int64_t ldx, const float* W, const floa
   p.B = W; p.ldb = K; p.b_mn = 0;
   p.C = y; p.ldc = ldy; p.M = M; p.N = N; p.K = K; p.bias = b; p.act = act; p.lim_dev = m_dev;
   p.err = ErrSink{nullptr, pm_tc_sticky_word()};
-  const dim3 grid(pm_cdiv(N, TBN), pm_cdiv(M, TBM), 1);
+  const dim3 grid(pm_cdiv(M, TBM), pm_cdiv(N, TBN), 1);
   int rc = precision == PM_PREC_BF16 ? launch_gemm_tc<1, EPI_FWD, false, false>(p, grid, pm_st(s))
                                      : launch_gemm_tc<3, EPI_FWD, false, false>(p, grid, pm_st(s));
   if (rc) return rc;
@@ -379,7 +379,7 @@ int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const flo
     p.A = dpre; p.lda = lddpre; p.a_mn = 1;         // A[K=rows x M=N'] : dpre as stored
     p.B = x; p.ldb = ldx; p.b_mn = 1;               // B[K=rows x N=K'] : x as stored
     p.C = part; p.ldc = K; p.M = N; p.N = K; p.K = M; p.lim_dev = m_dev; p.k_per_split = kps; p.err = sink;
-    const dim3 grid(pm_cdiv(K, TBN), pm_cdiv(N, TBM), splits);
+    const dim3 grid(pm_cdiv(N, TBM), pm_cdiv(K, TBN), splits);
     int rc = precision == PM_PREC_BF16 ? launch_gemm_tc<1, EPI_DW, true, true>(p, grid, st) : launch_gemm_tc<3, EPI_DW, true, true>(p, grid, st);
     if (rc) return rc;
     splitk_reduce_tc_kernel<<<pm_cdiv((int64_t)N * K, 256), 256, 0, st>>>(part, splits, (int64_t)N * K, dW);
@@ -394,7 +394,7 @@ int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const flo
     q.A = dpre; q.lda = lddpre; q.a_mn = 0;
     q.B = W; q.ldb = K; q.b_mn = 1;                 // B[K=N' x N=K'] : W as stored
     q.C = dx; q.ldc = lddx; q.M = M; q.N = K; q.K = N; q.act = act_prev; q.aux = x; q.ldaux = ldx; q.lim_dev = m_dev; q.err = sink;
-    const dim3 grid(pm_cdiv(K, TBN), pm_cdiv(M, TBM), 1);
+    const dim3 grid(pm_cdiv(M, TBM), pm_cdiv(K, TBN), 1);
     int rc = precision == PM_PREC_BF16 ? launch_gemm_tc<1, EPI_DX, false, true>(q, grid, st) : launch_gemm_tc<3, EPI_DX, false, true>(q, grid, st);
     if (rc) return rc;
   }
