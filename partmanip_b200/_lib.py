@@ -84,6 +84,9 @@ SIGNATURES = {
     "pm_conv3d_im2col": (I, [P, L, L, I, I, I, I, I, P, I, P]),
     "pm_conv3d_col2im": (I, [P, I, I, I, I, I, I, P, I, P, P]),
     "pm_conv3d_flatten": (I, [P, P, I, I, I, L, I, P]),
+    "pm_conv3d_first_forward": (I, [P, L, I, I, P, P, I, P, P]),
+    "pm_conv3d_first_backward_ws_bytes": (SZ, []),
+    "pm_conv3d_first_backward": (I, [P, L, I, I, P, P, P, P]),
     "pm_gather_rows": (I, [P, L, P, P, L, L, I, P]),
     "pm_copy_rows": (I, [P, L, P, L, L, I, P]),
 }

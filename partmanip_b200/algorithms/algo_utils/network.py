@@ -260,7 +260,7 @@ class _Conv3DRunner(_Runner):
             b = {"dev": dev, "dims": dims, "cols": [], "y": [], "dcols": [], "dpre": []}
             for i, (ci, co, k, s) in enumerate(self.SPECS):
                 rows, kpad = B * dims[i + 1] ** 3, (ci * k ** 3 + 3) // 4 * 4
-                b["cols"].append(torch.empty(rows, kpad, device=dev))
+                b["cols"].append(torch.empty(rows, kpad, device=dev) if i > 0 else None)    # layer 1 runs directly on the volume
                 b["y"].append(torch.empty(rows, co, device=dev))
                 b["dcols"].append(torch.empty(rows, kpad, device=dev) if i > 0 else None)
                 b["dpre"].append(torch.empty(rows, co, device=dev))
@@ -281,6 +281,10 @@ class _Conv3DRunner(_Runner):
         dims, act = buf["dims"], net.act_name
         src, ld_in, sstride = x, 1, x.stride(0)                      # the TSDF volume: one channel, voxels contiguous per sample
         for i, ((ci, co, k, s), conv) in enumerate(zip(self.SPECS, self._convs())):
+            if i == 0:       # one input channel: direct fp32 kernel on the raw volume, no 5 GB patch matrix
+                ops.conv3d_first_forward(x, dims[0], conv.weight.view(co, -1), conv.bias, act, buf["y"][0])
+                src, ld_in, sstride = buf["y"][0], co, dims[1] ** 3 * co
+                continue
             ops.conv3d_im2col(src, ld_in, sstride, B, ci, dims[i], k, s, buf["cols"][i])
             ops.linear_forward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), conv.bias, act, prec, out=buf["y"][i])
             src, ld_in, sstride = buf["y"][i], co, dims[i + 1] ** 3 * co
@@ -307,6 +311,9 @@ class _Conv3DRunner(_Runner):
         for i in (2, 1, 0):
             ci, co, k, s = self.SPECS[i]
             conv = self._convs()[i]
+            if i == 0:
+                ops.conv3d_first_backward(x, dims[0], buf["dpre"][0], grads[0].view(co, -1), grads[1])
+                continue
             ops.linear_backward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), buf["dpre"][i], grads[2 * i].view(co, -1),
                                    grads[2 * i + 1], buf["dcols"][i][:, :ci * k ** 3] if i > 0 else None, None, prec)
             if i > 0:

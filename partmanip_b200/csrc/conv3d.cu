@@ -82,6 +82,159 @@ flatten3d_kernel(const float* __restrict__ in, float* __restrict__ out, int B, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- first layer, direct
+// Conv3d(1, 16, k = 5, s = 3, p = 2) on the raw volume (network.py:70): one input channel — as a GEMM it would be a 10^7 x 125 patch
+// matrix (5 GB at 2048 samples) against a 16-column weight; done directly instead, in exact fp32 like the reference.
+// A CTA owns one output z-plane of one sample: the five input planes it needs sit in shared memory (zero-padded), the 125 x 16
+// weights too ([tap][channel], read as broadcast float4s); a thread owns output positions and all 16 channels.
+constexpr int C1_OUT = 16, C1_K = 5, C1_S = 3, C1_TAPS = 125, C1_THREADS = 320;
+
+// slab[kd][y][x] = vol[3*od - 2 + kd][y - 2][x - 2] (0 outside), y, x in [0, W): asynchronous 4-byte copies (cp.async with zero fill) —
+// every element's load is in flight at once (a plain load loop serialises on the ~700-cycle miss latency: 40 us per slab measured);
+// one integer division per row, none per element.  The caller waits with conv1_slab_wait().
+__device__ __forceinline__ void conv1_load_slab(float* slab, const float* __restrict__ vol, int Din, int W, int od) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < C1_K * W; r += nwarps) {
+    const int kd = r / W, y = r - kd * W;
+    const int id = od * C1_S - 2 + kd, ih = y - 2;
+    const bool row_ok = id >= 0 && id < Din && ih >= 0 && ih < Din;
+    const float* src = vol + ((int64_t)(row_ok ? id : 0) * Din + (row_ok ? ih : 0)) * Din;
+    for (int x = lane; x < W; x += 32) {
+      const int iw = x - 2;
+      const bool ok = row_ok && iw >= 0 && iw < Din;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab + r * W + x);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src + (ok ? iw : 0)), "r"(ok ? 4 : 0) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void conv1_slab_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(C1_THREADS)
+conv1_fwd_kernel(const float* __restrict__ x, int64_t ldx, int Din, int Dout, const float* __restrict__ w /* (16,125) */,
+                 const float* __restrict__ bias, int act, float* __restrict__ y /* ((b, od, oh, ow), 16) */) {
+  extern __shared__ __align__(16) float sm1[];
+  const int W = (Dout - 1) * C1_S + C1_K;
+  float* slab = sm1;
+  float4* wt = reinterpret_cast<float4*>(sm1 + ((C1_K * W * W + 3) / 4 * 4));    // [tap][4 x float4]
+  const int od = blockIdx.x, b = blockIdx.y;
+  conv1_load_slab(slab, x + (int64_t)b * ldx, Din, W, od);
+  for (int i = threadIdx.x; i < C1_TAPS * C1_OUT; i += blockDim.x) {
+    const int tap = i / C1_OUT, co = i - tap * C1_OUT;
+    reinterpret_cast<float*>(wt)[i] = w[co * C1_TAPS + tap];
+  }
+  conv1_slab_wait();
+  __syncthreads();
+  for (int pos = threadIdx.x; pos < Dout * Dout; pos += blockDim.x) {
+    const int oh = pos / Dout, ow = pos - oh * Dout;
+    float acc[C1_OUT];
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) acc[c] = bias[c];
+    const float* base = slab + (oh * C1_S) * W + ow * C1_S;
+#pragma unroll 1
+    for (int kd = 0; kd < C1_K; ++kd)
+#pragma unroll
+      for (int kh = 0; kh < C1_K; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < C1_K; ++kw) {
+          const float v = base[(kd * W + kh) * W + kw];
+          const float4* wr = wt + ((kd * C1_K + kh) * C1_K + kw) * 4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 ww = wr[q];
+            acc[4 * q] = fmaf(v, ww.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+          }
+        }
+    float4* dst = reinterpret_cast<float4*>(y + (((int64_t)b * Dout + od) * Dout * Dout + pos) * C1_OUT);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dst[q] = make_float4(pm_act_fwd(act, acc[4 * q]), pm_act_fwd(act, acc[4 * q + 1]), pm_act_fwd(act, acc[4 * q + 2]),
+                           pm_act_fwd(act, acc[4 * q + 3]));
+  }
+}
+
+// dW1[co][tap] partials: a persistent CTA walks (sample, output plane) pairs; thread = ((kd, kh) tap row, position group g of 4) keeps the
+// 5 x 16 accumulators of its five kw taps in registers and visits the positions pos = g (mod 4): per position 5 input loads + 4
+// broadcast float4 loads of dpre feed 80 FFMAs.  part[cta][g][tap][16]; the reduce kernel sums ctas and groups in a fixed order.
+constexpr int C1_DW_THREADS = 128, C1_DW_GROUPS = 4;
+__global__ void __launch_bounds__(C1_DW_THREADS)
+conv1_dw_kernel(const float* __restrict__ x, int64_t ldx, int B, int Din, int Dout, const float* __restrict__ dpre /* ((b,od,oh,ow),16) */,
+                float* __restrict__ part) {
+  extern __shared__ __align__(16) float sm1[];
+  const int W = (Dout - 1) * C1_S + C1_K, P2 = Dout * Dout;
+  float* slab = sm1;
+  float4* dp = reinterpret_cast<float4*>(sm1 + ((C1_K * W * W + 3) / 4 * 4));    // [pos][4 x float4]
+  int* off = reinterpret_cast<int*>(dp + P2 * 4);                                // [pos] = (3 oh) W + 3 ow
+  const int t = threadIdx.x, kdh = t % 25, g = t / 25;                           // threads >= 100 only help with the loads
+  const int row_off = ((kdh / 5) * W + (kdh % 5)) * W;
+  float acc[C1_K][C1_OUT];
+#pragma unroll
+  for (int kw = 0; kw < C1_K; ++kw)
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) acc[kw][c] = 0.f;
+  for (int pos = t; pos < P2; pos += blockDim.x) off[pos] = (pos / Dout) * C1_S * W + (pos % Dout) * C1_S;
+  const int64_t pairs = (int64_t)B * Dout;
+  for (int64_t pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+    const int b = (int)(pr / Dout), od = (int)(pr - (int64_t)b * Dout);
+    __syncthreads();                                                             // previous pair fully consumed
+    conv1_load_slab(slab, x + (int64_t)b * ldx, Din, W, od);
+    const float4* src = reinterpret_cast<const float4*>(dpre + ((int64_t)b * Dout + od) * P2 * C1_OUT);
+    for (int i = t; i < P2 * 4; i += blockDim.x) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dp + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    conv1_slab_wait();
+    __syncthreads();
+    if (g < C1_DW_GROUPS) {
+      for (int pos = g; pos < P2; pos += C1_DW_GROUPS) {
+        const float* in = slab + row_off + off[pos];
+        float v[C1_K];
+#pragma unroll
+        for (int kw = 0; kw < C1_K; ++kw) v[kw] = in[kw];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 d = dp[pos * 4 + q];
+#pragma unroll
+          for (int kw = 0; kw < C1_K; ++kw) {
+            acc[kw][4 * q] = fmaf(v[kw], d.x, acc[kw][4 * q]); acc[kw][4 * q + 1] = fmaf(v[kw], d.y, acc[kw][4 * q + 1]);
+            acc[kw][4 * q + 2] = fmaf(v[kw], d.z, acc[kw][4 * q + 2]); acc[kw][4 * q + 3] = fmaf(v[kw], d.w, acc[kw][4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (g < C1_DW_GROUPS) {
+#pragma unroll
+    for (int kw = 0; kw < C1_K; ++kw) {
+      float4* o = reinterpret_cast<float4*>(part + (((int64_t)blockIdx.x * C1_DW_GROUPS + g) * C1_TAPS + kdh * C1_K + kw) * C1_OUT);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[kw][4 * q], acc[kw][4 * q + 1], acc[kw][4 * q + 2], acc[kw][4 * q + 3]);
+    }
+  }
+}
+// dW1[co][tap] = sum over (cta, group) partials (one warp per output, lanes stride the partials, shuffle tree: fixed order)
+__global__ void __launch_bounds__(256)
+conv1_dw_reduce_kernel(const float* __restrict__ part, int n_part, float* __restrict__ dW) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= C1_TAPS * C1_OUT) return;
+  const int tap = i / C1_OUT, co = i - tap * C1_OUT;
+  float tsum = 0.f;
+  for (int c = lane; c < n_part; c += 32) tsum += part[((int64_t)c * C1_TAPS + tap) * C1_OUT + co];
+  tsum = pm_warp_sum(tsum);
+  if (lane == 0) dW[co * C1_TAPS + tap] = tsum;
+}
+inline size_t conv1_smem_fwd(int Dout) {
+  const int W = (Dout - 1) * C1_S + C1_K;
+  return ((size_t)(C1_K * W * W + 3) / 4 * 4 + C1_TAPS * C1_OUT) * sizeof(float);
+}
+inline size_t conv1_smem_dw(int Dout) {
+  const int W = (Dout - 1) * C1_S + C1_K;
+  return ((size_t)(C1_K * W * W + 3) / 4 * 4 + Dout * Dout * C1_OUT + Dout * Dout) * sizeof(float);
+}
+constexpr int C1_DW_CTAS = 3 * PM_NUM_SMS;
+
 inline int grid_for(int64_t total) {
   int64_t g = (total + 255) / 256;
   const int64_t cap = (int64_t)PM_NUM_SMS * 32;
@@ -114,6 +267,49 @@ int pm_conv3d_col2im(const float* dcols, int Kpad, int B, int C, int Din, int k,
   const int64_t rows = (int64_t)B * Din * Din * Din;
   col2im3d_kernel<<<grid_for(rows * C), 256, 0, pm_st(st)>>>(dcols, Kpad, C, Din, k, s, k / 2, Dout, rows, y, act, din);
   PM_CHECK_LAUNCH("pm_conv3d_col2im");
+  return PM_OK;
+}
+
+// first layer of the student, Conv3d(1, 16, 5, stride 3, padding 2) + activation, directly on the volume rows x (B, >= Din^3)
+int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, const float* w, const float* bias, int act, float* y,
+                            pm_stream_t st) {
+  PM_REQUIRE(x && w && bias && y && B > 0 && B <= 65535 && Din >= 3 && ldx >= (int64_t)Din * Din * Din, PM_ERR_ARG,
+             "pm_conv3d_first_forward: bad arguments (B=%d Din=%d)", B, Din);
+  PM_REQUIRE(act >= PM_ACT_NONE && act <= PM_ACT_SIGMOID, PM_ERR_ARG, "pm_conv3d_first_forward: activation %d", act);
+  const int Dout = pm_conv3d_out_dim(Din, C1_K, C1_S);
+  const size_t smem = conv1_smem_fwd(Dout);
+  PM_REQUIRE(smem <= 227 * 1024, PM_ERR_UNSUPPORTED, "pm_conv3d_first_forward: volume resolution %d needs %zu B of shared memory", Din, smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  conv1_fwd_kernel<<<dim3(Dout, B), C1_THREADS, smem, pm_st(st)>>>(x, ldx, Din, Dout, w, bias, act, y);
+  PM_CHECK_LAUNCH("pm_conv3d_first_forward");
+  return PM_OK;
+}
+
+size_t pm_conv3d_first_backward_ws_bytes(void) { return (size_t)C1_DW_CTAS * C1_DW_GROUPS * C1_TAPS * C1_OUT * sizeof(float); }
+
+// dW (16,1,5,5,5) of that layer from dpre ((b, voxel), 16) — no patch matrix; db is a column sum of dpre (pm_rms_colsum et al.)
+int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, const float* dpre, float* dW, void* ws, pm_stream_t st) {
+  PM_REQUIRE(x && dpre && dW && ws && B > 0 && Din >= 3, PM_ERR_ARG, "pm_conv3d_first_backward: bad arguments");
+  const int Dout = pm_conv3d_out_dim(Din, C1_K, C1_S);
+  const size_t smem = conv1_smem_dw(Dout);
+  PM_REQUIRE(smem <= 227 * 1024, PM_ERR_UNSUPPORTED, "pm_conv3d_first_backward: volume resolution %d needs %zu B of shared memory", Din, smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv1_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  float* part = reinterpret_cast<float*>(ws);
+  const int64_t pairs = (int64_t)B * Dout;
+  const int n_cta = (int)(pairs < C1_DW_CTAS ? pairs : C1_DW_CTAS);
+  conv1_dw_kernel<<<n_cta, C1_DW_THREADS, smem, pm_st(st)>>>(x, ldx, B, Din, Dout, dpre, part);
+  conv1_dw_reduce_kernel<<<pm_cdiv(C1_TAPS * C1_OUT, 8), 256, 0, pm_st(st)>>>(part, n_cta * C1_DW_GROUPS, dW);
+  PM_CHECK_LAUNCH("pm_conv3d_first_backward");
   return PM_OK;
 }
 

@@ -499,6 +499,22 @@ def conv3d_col2im(dcols: Tensor, B: int, C: int, Din: int, k: int, s: int, y: Te
     return din
 
 
+def conv3d_first_forward(x: Tensor, Din: int, w: Tensor, bias: Tensor, act, y: Tensor):
+    """Conv3d(1,16,5,stride 3,padding 2) + act on volume rows x (B, >= Din^3) -> y ((b, voxel'), 16), exact fp32."""
+    B, _, ldx = _rows(_f32(x, "x"), "x")
+    assert _f32(w, "w").is_contiguous() and w.numel() == 16 * 125 and _f32(y, "y").is_contiguous()
+    check(lib.pm_conv3d_first_forward(_p(x), ldx, B, int(Din), _p(w), _p(bias), PM_ACT[act], _p(y), _stream()), "pm_conv3d_first_forward")
+    return y
+
+
+def conv3d_first_backward(x: Tensor, Din: int, dpre: Tensor, dW: Tensor, db: Tensor):
+    B, _, ldx = _rows(_f32(x, "x"), "x")
+    assert _f32(dpre, "dpre").is_contiguous() and dpre.shape[1] == 16 and dW.is_contiguous() and dW.numel() == 16 * 125
+    ws = scratch(lib.pm_conv3d_first_backward_ws_bytes(), x.device, "conv1bwd")
+    check(lib.pm_conv3d_first_backward(_p(x), ldx, B, int(Din), _p(dpre), _p(dW), _p(ws), _stream()), "pm_conv3d_first_backward")
+    rms_colsum(dpre, db)
+
+
 def conv3d_flatten(src: Tensor, dst: Tensor, B: int, P: int, C: int, ld_row: int, to_rows: bool):
     check(lib.pm_conv3d_flatten(_p(_f32(src, "src")), _p(_f32(dst, "dst")), B, P, C, int(ld_row), int(bool(to_rows)), _stream()),
           "pm_conv3d_flatten")

@@ -23,8 +23,10 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
-for prec in ("fp32", "bf16"):
-    for B in (256, 2048):
+precs = sys.argv[1].split(",") if len(sys.argv) > 1 else ("fp32", "bf16")
+sizes = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else (256, 2048)
+for prec in precs:
+    for B in sizes:
         torch.manual_seed(0)
         net = Conv3DNet(125000, 10, dict(name="Conv3DNet", activation="tanh", precision=prec), 0).to(dev)
         xs = [torch.rand(B, 125000, device=dev) * 2 - 1 for _ in range(3)]
