@@ -367,6 +367,18 @@ int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, const 
  * to_rows == 0: out[(b*P + pos)*C + c] = in[b*ld_row + c*P + pos] */
 int pm_conv3d_flatten(const float* in, float* out, int B, int P, int C, int64_t ld_row, int to_rows, pm_stream_t st);
 
+/* ------------------------------------------------------------------------------------------
+ * NEXT ROW (third part): TSDF of the scene from per-part signed-distance grids (`mesh_tsdf` observations).
+ * replaces utils/mesh2sdf.py:119-139 (TSDFfromMesh.query_tsdf_parallel) + :239-272 (triplet_interpolation_query_parallel):
+ * sdf_field (M, field_stride) = the parts' grids padded with +1 to the common resolution (X, bbox_res_y, bbox_res_z) as
+ * merge_sdf_field builds them (:169-198), sdf_res (M,3) int32 each part's own resolution, sdf_voxel (M), sdf_bbox_min (M,3);
+ * pose_R (E,M,3,3), pose_T (E,M,3) part poses; init_tsdf (E, R^3) the volume the parts are min-ed into (metres, unscaled);
+ * out (E, R, R, R) = clamp(min(...) / (4 * size / R), -1, 1).  vox_origin: HOST array of 3.
+ * ------------------------------------------------------------------------------------------ */
+int pm_mesh2sdf_query(const float* sdf_field, int64_t field_stride, const int32_t* sdf_res, const float* sdf_voxel, const float* sdf_bbox_min,
+                      int M, int bbox_res_y, int bbox_res_z, const float* pose_R, const float* pose_T, const float* init_tsdf, int E,
+                      int resolution, const float* vox_origin, float size, float* out, pm_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

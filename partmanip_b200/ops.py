@@ -521,6 +521,26 @@ def conv3d_flatten(src: Tensor, dst: Tensor, B: int, P: int, C: int, ld_row: int
     return dst
 
 
+# ------------------------------------------------------------------------------------------- next row: mesh -> TSDF
+def mesh2sdf_query(sdf_field: Tensor, sdf_res: Tensor, sdf_voxel: Tensor, sdf_bbox_min: Tensor, bbox_res_y: int, bbox_res_z: int,
+                   pose_R: Tensor, pose_T: Tensor, init_tsdf: Tensor, resolution: int, vox_origin, size: float,
+                   out: Optional[Tensor] = None) -> Tensor:
+    """utils/mesh2sdf.py:119-139 + 239-272 in one launch -> (E, R, R, R)."""
+    E, M = pose_R.shape[0], pose_R.shape[1]
+    R = int(resolution)
+    assert _f32(sdf_field, "sdf_field").is_contiguous() and sdf_field.shape[0] == M and sdf_res.dtype == torch.int32 and sdf_res.shape == (M, 3)
+    assert _f32(pose_R, "pose_R").is_contiguous() and pose_R.shape == (E, M, 3, 3) and _f32(pose_T, "pose_T").is_contiguous() and pose_T.shape == (E, M, 3)
+    assert _f32(init_tsdf, "init_tsdf").is_contiguous() and init_tsdf.numel() == E * R ** 3
+    assert _f32(sdf_voxel, "sdf_voxel").numel() == M and _f32(sdf_bbox_min, "sdf_bbox_min").is_contiguous() and sdf_bbox_min.shape == (M, 3)
+    if out is None:
+        out = torch.empty(E, R, R, R, device=pose_R.device, dtype=torch.float32)
+    org = (ct.c_float * 3)(*[float(v) for v in vox_origin])
+    check(lib.pm_mesh2sdf_query(_p(sdf_field), sdf_field.shape[1], _p(sdf_res), _p(sdf_voxel), _p(sdf_bbox_min), M, int(bbox_res_y),
+                                int(bbox_res_z), _p(pose_R), _p(pose_T), _p(init_tsdf), E, R, org, float(size), _p(out), _stream()),
+          "pm_mesh2sdf_query")
+    return out
+
+
 # ------------------------------------------------------------------------------------------- next row: depth -> point cloud
 def depth2pc_backproject(depth: Tensor, cam_intr, cam_pose: Tensor, vol_origin, size: float, out: Optional[Tensor] = None) -> Tensor:
     """utils/depth2tsdf.py:146-159.  depth (E,M,H,W) fp32 CUDA, cam_pose (M,4,4) fp32 CUDA -> masked world cloud (E, M*H*W, 3)."""
