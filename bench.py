@@ -417,7 +417,10 @@ def main():
         iters_run = max(2, args.steps // 2) + e2e_warm
         e2e = {"value": E * T_STEPS * world / (ms_e2e * 1e-3), "unit": "env*steps/s",
                "h2d_bytes_per_step": int(env_h.h2d_bytes / iters_run), "d2h_bytes_per_step": int(env_h.d2h_bytes / iters_run),
-               "ms_per_step": ms_e2e}
+               "ms_per_step": ms_e2e,
+               "h2d": "every env step's observation is copied from pinned host memory inside the timed region, double-buffered on a copy "
+                      "stream so that the copy of step t+1 overlaps the learner's compute on step t (the synthetic pool does not depend "
+                      "on the actions); actions are copied back to the host every step"}
         del env_h, runner_h
 
     # ---- multi-GPU parity, part 2: world ranks x PARITY_E envs against the single-process run

@@ -60,7 +60,15 @@ class FakeVecEnv:
         E = num_envs
         if host:
             self._pool = [t.pin_memory() for t in self._pool]
-            self._obs_dev = torch.empty(E, D, device=self.device)
+            # two device buffers + a copy stream: the H2D copy of the NEXT pool entry runs while the learner computes on the current
+            # one.  Every copy still happens inside the caller's timed region and is counted in h2d_bytes; what the
+            # overlap models is a simulator that renders step t+1 concurrently with the learner — the pool does not depend on the
+            # actions, so the prefetch is exact here (a real env can only do this with one-step-stale actions).
+            self._obs_dev = [torch.empty(E, D, device=self.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._copied = [None, None]                # event: buffer i holds its pool entry
+            self._consumed = [None, None]              # event: the compute stream is done with buffer i
+            self._slot = 0
             self._act_host = torch.empty(E, num_actions).pin_memory()
         else:
             self._pool = [t.to(self.device) for t in self._pool]
@@ -81,15 +89,35 @@ class FakeVecEnv:
         k = self._k % len(self._pool)
         self._k += 1
         if self.host:
-            self._obs_dev.copy_(self._pool[k], non_blocking=True)
-            self.h2d_bytes += self._pool[k].numel() * 4
-            o = self._obs_dev
+            cur = torch.cuda.current_stream(self.device)
+            i = self._slot
+            if self._copied[i] is None:                 # first call: nothing prefetched yet
+                self._issue_copy(i, k, cur)
+            cur.wait_event(self._copied[i])             # the compute stream may read buffer i from here on
+            o = self._obs_dev[i]
+            # the OTHER buffer was handed out one call ago; everything the learner enqueued on it is ordered before this point
+            j = i ^ 1
+            self._consumed[j] = torch.cuda.Event()
+            self._consumed[j].record(cur)
+            self._issue_copy(j, (k + 1) % len(self._pool), cur)
+            self._slot = j
         else:
             o = self._pool[k]
         d = {self.obs_mode: o}
         for name, v in self._extra_pool.items():
             d[name] = v[k]
         return d
+
+    def _issue_copy(self, i, k, cur):
+        """H2D copy of pool entry k into device buffer i on the copy stream, after the compute stream has finished with buffer i."""
+        cs = self._copy_stream
+        if self._consumed[i] is not None:
+            cs.wait_event(self._consumed[i])
+        with torch.cuda.stream(cs):
+            self._obs_dev[i].copy_(self._pool[k], non_blocking=True)
+            self._copied[i] = torch.cuda.Event()
+            self._copied[i].record(cs)
+        self.h2d_bytes += self._pool[k].numel() * 4
 
     def reset(self):
         return self._obs()

@@ -296,7 +296,7 @@ def test_update_graph_is_dropped_when_a_workspace_moves():
             r.storage.compute_returns(last_values, r.gamma, r.lam)
             if disturb and it == 2:
                 assert r._graph is not None
-                ops.scratch(ops._scratch[(DEV, "adam")].numel() + 4096, DEV, "adam")   # somebody else grows a workspace the graph uses
+                ops.scratch(ops._scratch[(DEV, "loss")].numel() + 4096, DEV, "loss")   # somebody else grows a workspace the graph uses
             r.update(it + 1)
             if disturb and it == 2:
                 assert r._graph is None                                        # dropped, this update ran eagerly
