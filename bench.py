@@ -46,7 +46,7 @@ def ppo_cfg(E, device, precision, net=None, **over):
         test_only=False, save_pose=False, save_video=False, lr_schedule="fixed", lr=5e-5, desired_kl=0.1,
         epsilon_clip=0.2, gamma=0.99, lam=0.95, sampler="sequential", resume=None,
         cuda_graph=os.environ.get("PM_CUDA_GRAPH", "1") == "1", cuda_graph_multi_rank=os.environ.get("PM_CUDA_GRAPH_MULTI", "1") == "1",
-        fused_step=os.environ.get("PM_FUSED_STEP", "1") == "1",
+        fused_step=os.environ.get("PM_FUSED_STEP", "1") == "1", overlap_phases=os.environ.get("PM_OVERLAP", "1") == "1",
         tricks=dict(mini_adv_norm=False, whole_adv_norm=False, use_state_norm=True, use_clipped_value_loss=False,
                     use_grad_clip=True, max_grad_norm=0.5),
         model=dict(action_std=0.5, action_activate="tanh", clipAction=1.0,

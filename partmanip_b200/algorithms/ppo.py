@@ -218,6 +218,10 @@ class ppo:
         self.cuda_graph = bool(cfg.get('cuda_graph', True)) and cfg['sampler'] == 'sequential' and \
             (self.world == 1 or bool(cfg.get('cuda_graph_multi_rank', True)))
         self._graph, self._graph_calls, self._n_critic = None, 0, 0
+        # build extension: issue the (independent) actor and critic phases of the update on two streams — see _update_body
+        self.overlap_phases = bool(cfg.get('overlap_phases', True)) and cfg['sampler'] == 'sequential'
+        self._phase_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)) if self.overlap_phases else None
+        self._dbuf = {}
         self.resume(cfg['resume'])
 
     # ------------------------------------------------------------------ checkpoints (ppo.py:83-137)
@@ -424,61 +428,89 @@ class ppo:
             self._graph = None
             self._graph_calls = 0
 
-    def _update_body(self):
-        """The device-side part of update(): both phases over all epochs and minibatches (graph-capturable)."""
+    def _actor_step(self, mb, dmu, squash):
+        """One minibatch step of the actor phase (ppo.py:315-357)."""
         ac = self.actor_critic
-        world = self.world
+        inv_b = 1.0 / (mb['obs'].shape[0] * self.world)
+        mu = ac.actor.runner.forward(mb['obs'])
+        adv_stats = None
+        if self.tricks['mini_adv_norm']:
+            adv_stats = ops.normalize_stats(mb['adv'].reshape(-1), self._adv_stats)
+        ops.ppo_actor_loss(mu, ac.log_std.data, mb['act'], mb['logp'].reshape(-1), mb['mu'], mb['sigma'],
+                           mb['adv'].reshape(-1), adv_stats, inv_b, self.epsilon_clip, ac.max_action, squash,
+                           self._stats_a, dmu, self._actor_grads[-1])
+        ac.actor.runner.backward(mb['obs'], dmu, self._actor_grads[:-1])
+        if self.optimizer_actor.fused:     # all-reduce + rank-consistent KL-skip + clip + Adam: ONE launch
+            self.optimizer_actor.step_fused((inv_b, self.desired_kl, self._acc, self._skip))
+        else:
+            parallel.all_reduce_sum_(self.optimizer_actor.grad_ext)   # gradients + [sum surrogate, sum KL] in one collective
+            ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)   # rank-consistent KL-skip
+            self.optimizer_actor.step(self._skip)
+
+    def _critic_step(self, mb, dv):
+        """One minibatch step of the critic phase (ppo.py:359-384)."""
+        ac = self.actor_critic
+        inv_b = 1.0 / (mb['obs'].shape[0] * self.world)
+        v = ac.critic.runner.forward(mb['obs'])
+        clip_delta = None
+        if self.tricks['use_clipped_value_loss']:
+            ops.abs_sum(mb['val'].reshape(-1), self.epsilon_clip * inv_b, self._clip_delta)
+            parallel.all_reduce_sum_(self._clip_delta)
+            clip_delta = self._clip_delta
+        ops.value_loss(v, mb['ret'].reshape(-1), mb['val'].reshape(-1), clip_delta, inv_b, self._stats_v, dv)
+        ops.accumulate(self._stats_v, inv_b, self._acc, 4)
+        ac.critic.runner.backward(mb['obs'], dv, self._critic_grads)
+        if self.optimizer_critic.fused:
+            self.optimizer_critic.step_fused(None)
+        else:
+            parallel.all_reduce_sum_(self.optimizer_critic.grad)
+            self.optimizer_critic.step(None)
+
+    def _step_buffers(self, B):
+        buf = self._dbuf.get(B)
+        if buf is None:
+            buf = (torch.empty(B, self.num_actions, device=self.device), torch.empty(B, 1, device=self.device))
+            self._dbuf[B] = buf
+        return buf
+
+    def _update_body(self):
+        """The device-side part of update(): both phases over all epochs and minibatches (graph-capturable).
+
+        The reference runs the actor phase, then the critic phase (ppo.py:315-384).  The two phases touch disjoint state (different
+        networks, optimisers, accumulator slots; both only READ the rollout buffer), so with `overlap_phases` they are issued on two
+        streams, minibatch step by minibatch step: while one network sits in its small latency-bound kernels (head, loss, reduce,
+        fused step — and, multi-GPU, waits for its peers' gradients) the other network's encoder kernels fill the GPU.  Every
+        network sees exactly the sequence of operations it sees in the sequential order: results are bit-identical."""
+        squash = self.actor_critic.action_activate == 'tanh'
         self._acc.zero_()
         batch = self.storage.mini_batch_generator(self.num_mini_batches)
-        squash = ac.action_activate == 'tanh'
-        dmu = dv = None
-        # ---- phase 1: actor (ppo.py:315-357)
-        for epoch in range(self.n_updates):
-            for indices in batch:
-                mb = self._minibatch(indices)
-                B = mb['obs'].shape[0]
-                inv_b = 1.0 / (B * world)
-                if dmu is None or dmu.shape[0] != B:
-                    dmu = torch.empty(B, self.num_actions, device=self.device)
-                    dv = torch.empty(B, 1, device=self.device)
-                mu = ac.actor.runner.forward(mb['obs'])
-                adv_stats = None
-                if self.tricks['mini_adv_norm']:
-                    adv_stats = ops.normalize_stats(mb['adv'].reshape(-1), self._adv_stats)
-                ops.ppo_actor_loss(mu, ac.log_std.data, mb['act'], mb['logp'].reshape(-1), mb['mu'], mb['sigma'],
-                                   mb['adv'].reshape(-1), adv_stats, inv_b, self.epsilon_clip, ac.max_action, squash,
-                                   self._stats_a, dmu, self._actor_grads[-1])
-                ac.actor.runner.backward(mb['obs'], dmu, self._actor_grads[:-1])
-                if self.optimizer_actor.fused:     # all-reduce + rank-consistent KL-skip + clip + Adam: ONE launch
-                    self.optimizer_actor.step_fused((inv_b, self.desired_kl, self._acc, self._skip))
-                else:
-                    parallel.all_reduce_sum_(self.optimizer_actor.grad_ext)   # gradients + [sum surrogate, sum KL] in one collective
-                    ops.ppo_actor_finalize(self._stats_a, inv_b, self.desired_kl, self._acc, self._skip)   # rank-consistent KL-skip
-                    self.optimizer_actor.step(self._skip)
-        # ---- phase 2: critic (ppo.py:359-384)
         n_critic = 0
-        for epoch in range(self.n_updates):
-            for indices in batch:
-                mb = self._minibatch(indices)
-                B = mb['obs'].shape[0]
-                inv_b = 1.0 / (B * world)
-                if dv is None or dv.shape[0] != B:
-                    dv = torch.empty(B, 1, device=self.device)
-                v = ac.critic.runner.forward(mb['obs'])
-                clip_delta = None
-                if self.tricks['use_clipped_value_loss']:
-                    ops.abs_sum(mb['val'].reshape(-1), self.epsilon_clip * inv_b, self._clip_delta)
-                    parallel.all_reduce_sum_(self._clip_delta)
-                    clip_delta = self._clip_delta
-                ops.value_loss(v, mb['ret'].reshape(-1), mb['val'].reshape(-1), clip_delta, inv_b, self._stats_v, dv)
-                ops.accumulate(self._stats_v, inv_b, self._acc, 4)
-                ac.critic.runner.backward(mb['obs'], dv, self._critic_grads)
-                if self.optimizer_critic.fused:
-                    self.optimizer_critic.step_fused(None)
-                else:
-                    parallel.all_reduce_sum_(self.optimizer_critic.grad)
-                    self.optimizer_critic.step(None)
-                n_critic += 1
+        if self.overlap_phases and self.storage.sampler == "sequential":
+            cur = torch.cuda.current_stream()
+            sa, sc = self._phase_streams
+            sa.wait_stream(cur)
+            sc.wait_stream(cur)
+            for epoch in range(self.n_updates):
+                for indices in batch:
+                    mb = self._minibatch(indices)
+                    dmu, dv = self._step_buffers(mb['obs'].shape[0])
+                    with torch.cuda.stream(sa), ops.scratch_ns("actor/"):
+                        self._actor_step(mb, dmu, squash)
+                    with torch.cuda.stream(sc), ops.scratch_ns("critic/"):
+                        self._critic_step(mb, dv)
+                    n_critic += 1
+            cur.wait_stream(sa)
+            cur.wait_stream(sc)
+        else:
+            for epoch in range(self.n_updates):          # ---- phase 1: actor
+                for indices in batch:
+                    mb = self._minibatch(indices)
+                    self._actor_step(mb, self._step_buffers(mb['obs'].shape[0])[0], squash)
+            for epoch in range(self.n_updates):          # ---- phase 2: critic
+                for indices in batch:
+                    mb = self._minibatch(indices)
+                    self._critic_step(mb, self._step_buffers(mb['obs'].shape[0])[1])
+                    n_critic += 1
         parallel.all_reduce_sum_(self._acc[4:5])
         self._n_critic = n_critic
 

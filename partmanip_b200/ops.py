@@ -63,9 +63,27 @@ def scratch_generation() -> int:
     return _scratch_gen[0]
 
 
+_scratch_ns = [""]
+
+
+class scratch_ns:
+    """`with ops.scratch_ns("critic"):` — workspaces requested inside get their own copies, so that two kernel sequences that run
+    CONCURRENTLY on different streams (the actor and the critic phase of the PPO update) never share a scratch buffer."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        self.prev, _scratch_ns[0] = _scratch_ns[0], self.name
+        return self
+
+    def __exit__(self, *a):
+        _scratch_ns[0] = self.prev
+
+
 def scratch(nbytes: int, device, tag: str = "default") -> Tensor:
-    """Grow-only per-(device, tag) byte workspace (never shrinks, never shared across tags)."""
-    key = (str(device), tag)
+    """Grow-only per-(device, namespace + tag) byte workspace (never shrinks, never shared across tags)."""
+    key = (str(device), _scratch_ns[0] + tag)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():

@@ -296,7 +296,9 @@ def test_update_graph_is_dropped_when_a_workspace_moves():
             r.storage.compute_returns(last_values, r.gamma, r.lam)
             if disturb and it == 2:
                 assert r._graph is not None
-                ops.scratch(ops._scratch[(DEV, "loss")].numel() + 4096, DEV, "loss")   # somebody else grows a workspace the graph uses
+                key = next(k for k in ops._scratch if k[0] == DEV and k[1].endswith("loss"))       # ("cuda:0", "actor/loss") when the phases overlap
+                with ops.scratch_ns(key[1][:-len("loss")]):
+                    ops.scratch(ops._scratch[key].numel() + 4096, DEV, "loss")   # somebody else grows a workspace the graph uses
             r.update(it + 1)
             if disturb and it == 2:
                 assert r._graph is None                                        # dropped, this update ran eagerly
