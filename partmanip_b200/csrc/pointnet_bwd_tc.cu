@@ -50,7 +50,7 @@ constexpr uint32_t SB_TOTAL = 204288 + 64;
 constexpr uint32_t TC_DB2 = 128;         // + hh*16: dPre2^T . Xe for h2-channel half hh
 constexpr uint32_t TC_DW1 = 160;         // dPre1^T . Xe
 
-enum { BAR_ACC2_FULL = 0, BAR_ACC1_FULL, BAR_M4_FULL, NUM_BARS };
+enum { BAR_ACC2_FULL = 0, BAR_ACC1_FULL, BAR_M4_FULL, BAR_W_LOADED, NUM_BARS };
 
 // ---- per-CTA partial-gradient record (floats)
 constexpr int PW2 = 0;                   // [256][128]
@@ -123,12 +123,6 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   // ---------------- prologue
   if ((sbase & 1023u) != 0 && tid == 0) err_report(err, 900);
   {
-    const uint4* src = reinterpret_cast<const uint4*>(w2img);
-    uint4* dst = reinterpret_cast<uint4*>(smem + SB_W2);
-    for (int i = tid; i < (int)(W2IMG_BYTES / 16); i += BT_THREADS) dst[i] = __ldg(src + i);
-    const uint4* src3 = reinterpret_cast<const uint4*>(w3pack + (size_t)cb * 8192);
-    uint4* dst3 = reinterpret_cast<uint4*>(smem + SB_W3);
-    for (int i = tid; i < 32768 / 16; i += BT_THREADS) dst3[i] = __ldg(src3 + i);
     for (int i = tid; i < 128; i += BT_THREADS) {
       float w[4] = {0.f, 0.f, 0.f, 0.f};
       for (int c = 0; c < C; ++c) w[c] = W1[i * C + c];
@@ -141,6 +135,11 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   if (tid == 0) {
     for (int i = 0; i < NUM_BARS; ++i) mbar_init(bar(i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // resident weight images through the TMA engine: W2 (64 KB) + this CTA's W3 channel block (32 KB), 16 KB bulk copies
+    mbar_expect_tx(bar(BAR_W_LOADED), (uint32_t)(W2IMG_BYTES + 32768));
+    for (uint32_t off = 0; off < (uint32_t)W2IMG_BYTES; off += 16384u) bulk_g2s(sbase + SB_W2 + off, w2img + off, 16384u, bar(BAR_W_LOADED));
+    const uint8_t* src3 = reinterpret_cast<const uint8_t*>(w3pack + (size_t)cb * 8192);
+    for (uint32_t off = 0; off < 32768u; off += 16384u) bulk_g2s(sbase + SB_W3 + off, src3 + off, 16384u, bar(BAR_W_LOADED));
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
@@ -151,7 +150,7 @@ encoder_bwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  bool ok = true;
+  bool ok = mbar_wait(bar(BAR_W_LOADED), 0, err, 210);
 
   const uint32_t idesc_m1 = umma_idesc_ex(128, 256, 0, 0);
   const uint32_t idesc_m3 = umma_idesc_ex(128, 128, 0, 1);

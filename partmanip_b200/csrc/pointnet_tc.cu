@@ -41,7 +41,7 @@ constexpr uint32_t SM_TOTAL = 232064;
 constexpr uint32_t KBLOCK_BYTES = 128 * 128;   // one 64-wide k-block of a 128-row operand
 
 enum { BAR_H1_FULL = 0, BAR_ACC2_FULL, BAR_H2_KB0, BAR_H2_KB1, BAR_H2_KB2, BAR_H2_KB3, BAR_G_FULL0, BAR_G_FULL1,
-       BAR_G_EMPTY0, BAR_G_EMPTY1, BAR_L3_DONE, NUM_BARS };
+       BAR_G_EMPTY0, BAR_G_EMPTY1, BAR_L3_DONE, BAR_W_LOADED, NUM_BARS };
 // TMEM plan: two 256-column regions that swap roles every tile (p = tile parity):
 //   region p   : layer-2 accumulator of this tile, then (once E2 has read it) layer-3 group 1 (channel chunk 1)
 //   region p^1 : layer-3 group 0 (channel chunk 0) of this tile; it held group 1 of the previous tile
@@ -165,11 +165,16 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
   // ---------------- prologue: resident weights, barriers, TMEM
   if ((sbase & 1023u) != 0 && tid == 0) err_report(err, 900);
   {
-    const uint4* src = reinterpret_cast<const uint4*>(wpack + (size_t)rank * WPACK_PER_RANK);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < (int)(WPACK_PER_RANK / 16); i += TC_THREADS) dst[i] = __ldg(src + i);
     for (int i = tid; i < 128 * 4; i += TC_THREADS) sW1[i] = ((i & 3) < C) ? W1[(i >> 2) * C + (i & 3)] : 0.f;
     if (tid < 128) sB1[tid] = b1[tid];
+  }
+  if (tid == 0) {
+    // the CTA's resident weight image (160 KB) comes in through the TMA engine: ten 16 KB bulk copies on one mbarrier
+    mbar_init(bar(BAR_W_LOADED), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar(BAR_W_LOADED), (uint32_t)WPACK_PER_RANK);
+    const uint8_t* src = wpack + (size_t)rank * WPACK_PER_RANK;
+    for (uint32_t off = 0; off < (uint32_t)WPACK_PER_RANK; off += 16384u) bulk_g2s(sbase + off, src + off, 16384u, bar(BAR_W_LOADED));
   }
   if (tid == 0) {
     mbar_init(bar(BAR_H1_FULL), 4);
@@ -183,13 +188,12 @@ encoder_fwd_tc(const float* __restrict__ x, int64_t ldx, int B, int N, int C, co
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  fence_proxy_async();          // weight images were written with generic-proxy stores; the MMA reads via the async proxy
   tc_fence_before();
   __syncthreads();
+  bool ok = mbar_wait(bar(BAR_W_LOADED), 0, err, 110);          // weight images landed (async proxy wrote them; the MMA reads them via the same proxy)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  bool ok = true;
 
   // ---- layer-2 epilogue: acc row -> +b2 -> act -> bf16 -> smem.  Each of the four epilogue groups takes the SAME 16-column
   //      slice (slice = group index) of every 64-channel k-block of H2, so the k-blocks complete one after the other (not all

@@ -50,14 +50,6 @@ __host__ __device__ constexpr uint32_t region_col(int p) { return p ? 256u : 0u;
 
 constexpr size_t WIMG_PER_RANK = (size_t)STAGES_PER_TILE * KB;      // 320 KB
 
-// ---- TMA (bulk, non-tensor) helpers
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 // instruction descriptor: D = f32, A = B = f16, both K-major, dense
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
