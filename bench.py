@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     ap.add_argument("--cpu-baseline-envs", type=int, default=64)
     ap.add_argument("--gpu-baseline-iters", type=int, default=10)
-    ap.add_argument("--gpu-baseline-budget-s", type=float, default=150.0)
+    ap.add_argument("--gpu-baseline-budget-s", type=float, default=75.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip modes.fp32 / configs (DAgger, state-MLP)")
@@ -493,7 +493,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         Ec = args.cpu_baseline_envs
-        v, t, n = cpu_port_iteration(Ec, threads, iters=2, warm=1, budget_s=40.0)
+        v, t, n = cpu_port_iteration(Ec, threads, iters=2, warm=1, budget_s=5.0)
         cpu_baseline = {"value": v, "unit": "env*steps/s", "cores": threads, "kind": "port",
                         "sample": f"{n} full PPO iteration(s) at E={Ec} envs x {N_PTS} pts after 1 warm-up ({t:.1f} s each) with the CPU oracle port"}
 

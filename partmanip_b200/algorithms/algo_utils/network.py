@@ -175,7 +175,7 @@ class _PointNetRunner(_Runner):
         f = net.final_mlp
         if net.output_dim <= 32 and _FUSED_HEAD:      # fused head: one launch
             return ops.pointnet_head_forward(feat, self.head_params(), net.output_dim, net.act_name, buf["h1"], buf["h2"],
-                                             buf["out"], precision=net.head_precision)
+                                             buf["out"])
         ops.linear_forward(feat, f[0].weight, f[0].bias, net.act_name, out=buf["h1"])
         ops.linear_forward(buf["h1"], f[2].weight, f[2].bias, net.act_name, out=buf["h2"])
         return ops.linear_forward(buf["h2"], f[4].weight, f[4].bias, None, out=buf["out"])
@@ -189,8 +189,7 @@ class _PointNetRunner(_Runner):
         f = net.final_mlp
         if net.output_dim <= 32 and _FUSED_HEAD:      # fused head backward: three launches
             ops.pointnet_head_backward(buf["feat"], self.head_params(), net.output_dim, net.act_name, buf["h1"], buf["h2"],
-                                       dout, grads[6:12], buf["dfeat"], 512 * (1 + net.max_mean_concat),
-                                       precision=net.head_precision)
+                                       dout, grads[6:12], buf["dfeat"], 512 * (1 + net.max_mean_concat))
         else:
             ops.linear_backward(buf["h2"], f[4].weight, dout, grads[10], grads[11], buf["dh2"], net.act_name)
             ops.linear_backward(buf["h1"], f[2].weight, buf["dh2"], grads[8], grads[9], buf["dh1"], net.act_name)
@@ -206,8 +205,8 @@ class PointNet(nn.Module):
     [cat proprio], head Linear(F,128)-act-Linear(128,32)-act-Linear(32,out).  PyTorch default Linear init.
 
     Build extensions over the reference (which hard-codes point_num=1024, network.py:146): `net_cfg['point_num']`
-    (default 1024), `net_cfg['precision']` in {"fp32","bf16"} (encoder, default "fp32") and `net_cfg['head_precision']`
-    (head GEMMs, default "fp32")."""
+    (default 1024) and `net_cfg['precision']` (encoder): "fp32" (default; split-operand tcgen05 kernels at the reference's
+    precision), "bf16" (tcgen05, 1e-2 gate) or "fp32_ffma" (CUDA cores only).  The head is fp32 in every mode."""
 
     def __init__(self, input_dim, output_dim, net_cfg, proprio_shape=0):
         super().__init__()
@@ -233,11 +232,6 @@ class PointNet(nn.Module):
         self.precision = net_cfg.get('precision', 'fp32')
         if self.precision not in ("fp32", "bf16", "fp32_ffma"):
             raise NotImplementedError(f"precision {self.precision!r}")
-        # the head (0.04 % of the FLOPs) stays on the fp32 FFMA kernels by default: its tcgen05 variant (head_tc.cu,
-        # `head_precision: bf16`) measured no faster at B = 2048 (16-32 CTAs, staging-latency bound) and costs accuracy
-        self.head_precision = net_cfg.get('head_precision', 'fp32')
-        if self.head_precision not in ("fp32", "bf16"):
-            raise NotImplementedError(f"head_precision {self.head_precision!r}")
         self.feat_dim = 512 * (1 + self.max_mean_concat) + proprio_shape
         self.runner = _PointNetRunner(self)
 

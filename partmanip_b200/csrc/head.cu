@@ -9,11 +9,6 @@
 //   reduce fixed-order sums of the partials (deterministic; no atomics)
 #include "common.cuh"
 
-extern "C" int pm_head_fwd_tc_launch(const float* feat, int64_t ldf, int B, int F, const pm_head_params* p, int out_dim, int act,
-                                     float* h1, float* h2, float* out, int64_t ldo, int32_t* err, cudaStream_t st);
-extern "C" int pm_head_bwd_tc_launch(const float* dpre1, const float* feat, int64_t ldf, int B, int F, const float* W0, float* dfeat,
-                                     int64_t lddf, int dfeat_cols, float* partB, int32_t* err, cudaStream_t st);
-
 namespace {
 
 constexpr int HR = 16;            // batch rows per CTA
@@ -329,14 +324,9 @@ int pm_pointnet_head_forward(const float* feat, int64_t ldf, int B, int F, const
   PM_REQUIRE(feat && p && h1 && h2 && out, PM_ERR_ARG, "pm_pointnet_head_forward: null pointer");
   PM_REQUIRE(B > 0 && F > 0 && ldf >= F && out_dim >= 1 && out_dim <= OMAX && ldo >= out_dim, PM_ERR_SHAPE,
              "pm_pointnet_head_forward: B=%d F=%d out=%d (out <= %d)", B, F, out_dim, OMAX);
-  PM_REQUIRE(precision == PM_PREC_FP32 || precision == PM_PREC_BF16, PM_ERR_ARG, "pm_pointnet_head_forward: precision %d", precision);
-  if (precision == PM_PREC_BF16) {
-    PM_REQUIRE(pm_aligned(h1, 16) && pm_aligned(h2, 16), PM_ERR_ALIGN, "pm_pointnet_head_forward: h1/h2 must be 16-byte aligned");
-    int rc = pm_head_fwd_tc_launch(feat, ldf, B, F, p, out_dim, act, h1, h2, out, ldo, nullptr, pm_st(s));
-    if (rc) return rc;
-    PM_CHECK_LAUNCH("pm_pointnet_head_forward(bf16)");
-    return PM_OK;
-  }
+  // the head (0.04 % of the network's FLOPs) is fp32 on CUDA cores in every mode: a tcgen05 variant (round 1) was no faster at
+  // B = 2048 — 16-32 CTAs, staging-latency bound — and was removed
+  PM_REQUIRE(precision == PM_PREC_FP32 || precision == PM_PREC_FP32_FFMA, PM_ERR_UNSUPPORTED, "pm_pointnet_head_forward: precision %d (the head runs in fp32)", precision);
 #define PM_HF(ACTV)                                                                                                      \
   case ACTV: {                                                                                                           \
     static bool attr_set = false;                                                                                        \
@@ -367,12 +357,11 @@ int pm_pointnet_head_backward(const float* feat, int64_t ldf, int B, int F, cons
   PM_REQUIRE(B > 0 && F > 0 && ldf >= F && out_dim >= 1 && out_dim <= OMAX && lddo >= out_dim, PM_ERR_SHAPE,
              "pm_pointnet_head_backward: B=%d F=%d out=%d (out <= %d)", B, F, out_dim, OMAX);
   PM_REQUIRE(!dfeat || (dfeat_cols > 0 && dfeat_cols <= F && lddf >= dfeat_cols), PM_ERR_SHAPE, "pm_pointnet_head_backward: dfeat_cols=%d", dfeat_cols);
-  PM_REQUIRE(precision == PM_PREC_FP32 || precision == PM_PREC_BF16, PM_ERR_ARG, "pm_pointnet_head_backward: precision %d", precision);
+  PM_REQUIRE(precision == PM_PREC_FP32 || precision == PM_PREC_FP32_FFMA, PM_ERR_UNSUPPORTED, "pm_pointnet_head_backward: precision %d (the head runs in fp32)", precision);
   HeadWs w = carve_head(ws, B, F);
   PM_REQUIRE(ws_bytes >= w.total, PM_ERR_ARG, "pm_pointnet_head_backward: workspace %zu < %zu", ws_bytes, w.total);
   cudaStream_t st = pm_st(s);
-  const bool tc = precision == PM_PREC_BF16;
-  float* dfeat_ffma = tc ? nullptr : dfeat;          // bf16: dfeat and dW0 come from the tcgen05 GEMMs (head_tc.cu)
+  float* dfeat_ffma = dfeat;
 #define PM_HB(ACTV)                                                                                                      \
   case ACTV: {                                                                                                           \
     static bool attr_set = false;                                                                                        \
@@ -390,14 +379,8 @@ int pm_pointnet_head_backward(const float* feat, int64_t ldf, int B, int F, cons
     default: PM_FAIL(PM_ERR_ARG, "pm_pointnet_head_backward: activation %d", act);
   }
 #undef PM_HB
-  int slabs = w.slabs;
-  if (tc) {
-    int rc = pm_head_bwd_tc_launch(w.dpre1, feat, ldf, B, F, p->W0, dfeat, lddf, dfeat_cols, w.partB, nullptr, st);
-    if (rc) return rc;
-    slabs = pm_cdiv(B, 128);                        // the tcgen05 dW0 kernel works on 128-row slabs
-  } else {
-    head_bwd_b_kernel<<<dim3(pm_cdiv(F, CBK), w.slabs), HT, 0, st>>>(feat, ldf, B, F, w.dpre1, w.partB);
-  }
+  const int slabs = w.slabs;
+  head_bwd_b_kernel<<<dim3(pm_cdiv(F, CBK), w.slabs), HT, 0, st>>>(feat, ldf, B, F, w.dpre1, w.partB);
   const int n_out = H1D * F + H2D * H1D + H2D + out_dim * H2D + out_dim + H1D;
   head_reduce_kernel<<<pm_cdiv(n_out, 256), 256, 0, st>>>(w.partA, w.nA, w.partB, slabs, F, out_dim, *g);
   PM_CHECK_LAUNCH("pm_pointnet_head_backward");

@@ -241,53 +241,3 @@ def test_empty_batch_is_rejected():
     net = PointNet(3072, 10, dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False), 0).to(DEV)
     with pytest.raises(ValueError, match="empty batch"):
         net(torch.empty(0, 3072, device=DEV))
-
-
-@pytest.mark.parametrize("B,F,out,act,cols", [(2048, 512, 10, "tanh", 512), (37, 537, 1, "elu", 512), (5, 1024, 7, "relu", 1024),
-                                              (300, 512, 32, "tanh", 512), (1, 512, 10, "sigmoid", 512), (129, 512, 1, "tanh", 512)])
-def test_tc_head_forward_backward_vs_torch(B, F, out, act, cols):
-    """K3c: the head's GEMMs on tcgen05 (bf16 operands, fp32 accumulation) against torch autograd in fp32: outputs within
-    the bf16 gate, every gradient tensor within 2 % relative L2 (operand rounding 2^-9 averaged over 128..2048 terms)."""
-    if not _has_tc():
-        pytest.skip("library built without the tcgen05 kernels")
-    from partmanip_b200 import ops
-    torch.manual_seed(B + F + out)
-    f = {"tanh": torch.tanh, "elu": torch.nn.functional.elu, "relu": torch.relu, "sigmoid": torch.sigmoid}[act]
-    feat = torch.randn(B, F, requires_grad=True)
-    Ws = [(torch.randn(128, F) / F ** 0.5), torch.randn(128) * 0.1, torch.randn(32, 128) / 128 ** 0.5, torch.randn(32) * 0.1,
-          torch.randn(out, 32) / 32 ** 0.5, torch.randn(out) * 0.1]
-    Ws = [w.requires_grad_(True) for w in Ws]
-    h1 = f(feat @ Ws[0].T + Ws[1]); h2 = f(h1 @ Ws[2].T + Ws[3]); y = h2 @ Ws[4].T + Ws[5]
-    dout = torch.randn(B, out)
-    y.backward(dout)
-    dW = [cu(w.detach()) for w in Ws]
-    g = [torch.full_like(w, float("nan")) for w in dW]
-    h1d, h2d, yd = torch.empty(B, 128, device=DEV), torch.empty(B, 32, device=DEV), torch.empty(B, out, device=DEV)
-    featd = cu(feat.detach())
-    ops.pointnet_head_forward(featd, dW, out, act, h1d, h2d, yd, precision="bf16")
-    assert close(yd.cpu(), y.detach(), 1e-2, 1e-2), max_err(yd.cpu(), y.detach())
-    assert close(h1d.cpu(), h1.detach(), 1e-2, 1e-2) and close(h2d.cpu(), h2.detach(), 1e-2, 1e-2)
-    dfeat = torch.full((B, cols), float("nan"), device=DEV)
-    ops.pointnet_head_backward(featd, dW, out, act, h1d, h2d, cu(dout), g, dfeat, cols, precision="bf16")
-    rel = lambda a, b: float((a.cpu() - b).norm() / (b.norm() + 1e-20))
-    for got, w in zip(g, Ws):
-        assert bool(torch.isfinite(got).all()) and rel(got, w.grad) < 2e-2, (tuple(w.shape), rel(got, w.grad))
-    assert bool(torch.isfinite(dfeat).all()) and rel(dfeat, feat.grad[:, :cols]) < 2e-2, rel(dfeat, feat.grad[:, :cols])
-
-
-def test_tc_pointnet_with_tc_head_golden():
-    """`head_precision: bf16` end to end (tcgen05 encoder + tcgen05 head) against the reference recording."""
-    if not _has_tc():
-        pytest.skip("library built without the tcgen05 kernels")
-    from partmanip_b200.algorithms.algo_utils.network import PointNet
-    g = load_golden("pointnet_base_a10.npz")
-    net = PointNet(3072, 10, dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, precision="bf16",
-                                  head_precision="bf16"), 0)
-    net.load_state_dict(sub(g, "w"))
-    net.to(DEV)
-    y = net(cu(g["x"]))
-    assert close(y.detach().cpu(), g["y"], 1e-2, 1e-2), max_err(y.detach().cpu(), g["y"])
-    y.square().sum().backward()
-    for k, v in sub(g, "g").items():
-        got = dict(net.named_parameters())[k].grad.cpu()
-        assert bool(torch.isfinite(got).all()) and float((got - v).norm() / (v.norm() + 1e-12)) < 0.1, k
