@@ -23,9 +23,9 @@ int32_t* pm_tc_sticky_word();
 
 namespace {
 
-constexpr int FS_THREADS = 256;
-constexpr int FS_MAX_WORLD = 16;
-constexpr int FLAG_DONE = 32;             // uint32 index of D[0] inside a rank's flag buffer (R[0..16) at 0)
+constexpr int FS_THREADS = 512;
+constexpr int FS_MAX_WORLD = 8;
+constexpr int FLAG_DONE = 32;             // uint32 index of D[0] inside a rank's flag buffer (R[0..8) at 0)
 
 struct FusedStepP {
   float* params; float* exp_avg; float* exp_avg_sq;
@@ -108,15 +108,24 @@ fused_step_kernel(const FusedStepP p) {
   const int64_t i0 = min(total, (int64_t)blockIdx.x * per), i1 = min(total, i0 + per);
   double sq = 0.0;
   if (s_ok) {
+    // peer pointers into registers once (the table itself sits in device memory)
+    const float* peer[FS_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < FS_MAX_WORLD; ++r) peer[r] = (p.world > 1 && r < p.world) ? p.grad_peers[r] : p.grad_local;
     for (int64_t i = i0 + 4 * tid; i < i1; i += 4 * FS_THREADS) {
       float4 g;
       if (i + 4 <= i1) {
         if (p.world > 1) {
-          g = ld_peer4(p.grad_peers[0] + i);
-          for (int r = 1; r < p.world; ++r) {
-            const float4 h = ld_peer4(p.grad_peers[r] + i);
-            g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
-          }
+          // all peers' loads of this position are issued before the first add (NVLink round trip ~2 us: latency, not bandwidth,
+          // bounds the pull), then summed in rank order
+          float4 h[FS_MAX_WORLD];
+#pragma unroll
+          for (int r = 0; r < FS_MAX_WORLD; ++r)
+            if (r < p.world) h[r] = ld_peer4(peer[r] + i);
+          g = h[0];
+#pragma unroll
+          for (int r = 1; r < FS_MAX_WORLD; ++r)
+            if (r < p.world) { g.x += h[r].x; g.y += h[r].y; g.z += h[r].z; g.w += h[r].w; }
         } else {
           g = *reinterpret_cast<const float4*>(p.grad_local + i);
         }
