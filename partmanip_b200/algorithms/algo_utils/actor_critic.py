@@ -103,31 +103,31 @@ class ActorCritic(nn.Module):
 
     @torch.no_grad()
     def cri(self, observations):
-        return self.critic.runner.forward(observations).clone()
+        return self.critic.runner.forward(observations, need_backward=False).clone()
 
     @torch.no_grad()
     def random_act_cri(self, observations, eps: Optional[torch.Tensor] = None):
         """actor_critic.py:36-47.  `eps` (E,A) optionally injects the standard-normal draw (parity tests)."""
-        mu = self.actor.runner.forward(observations)
+        mu = self.actor.runner.forward(observations, need_backward=False)
         actions, logp, sigma = ops.policy_sample(mu, self.log_std.data, self._eps(mu, eps), self.max_action, self._squash)
-        value = self.critic.runner.forward(observations)
+        value = self.critic.runner.forward(observations, need_backward=False)
         return actions, logp, value.clone(), mu.clone(), sigma
 
     @torch.no_grad()
     def random_act(self, observations, eps: Optional[torch.Tensor] = None):
-        mu = self.actor.runner.forward(observations)
+        mu = self.actor.runner.forward(observations, need_backward=False)
         actions, _, _ = ops.policy_sample(mu, self.log_std.data, self._eps(mu, eps), self.max_action, self._squash)
         return actions
 
     @torch.no_grad()
     def act(self, observations):
-        mu = self.actor.runner.forward(observations)
+        mu = self.actor.runner.forward(observations, need_backward=False)
         return ops.action_activation(mu, self.max_action, self._squash)
 
     @torch.no_grad()
     def act_cri(self, observations):
-        mu = self.actor.runner.forward(observations)
-        value = self.critic.runner.forward(observations)
+        mu = self.actor.runner.forward(observations, need_backward=False)
+        value = self.critic.runner.forward(observations, need_backward=False)
         return ops.action_activation(mu, self.max_action, self._squash), value.clone()
 
     @torch.no_grad()

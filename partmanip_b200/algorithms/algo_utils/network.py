@@ -61,7 +61,7 @@ class _MLPRunner(_Runner):
             self._bufs[B] = b
         return b
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, need_backward: bool = True) -> torch.Tensor:
         net = self.net
         B = x.shape[0]
         buf = self._get(B, x.device)
@@ -158,7 +158,8 @@ class _PointNetRunner(_Runner):
         f = self.net.final_mlp
         return [f[0].weight, f[0].bias, f[2].weight, f[2].bias, f[4].weight, f[4].bias]
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, need_backward: bool = True) -> torch.Tensor:
+        """need_backward=False (rollout / evaluation): the encoder skips the argmax bookkeeping of the max-pool."""
         net = self.net
         B = x.shape[0]
         N, C, p = net.point_num, net.in_channels, net.proprio_shape
@@ -169,7 +170,7 @@ class _PointNetRunner(_Runner):
         fmean = feat[:, 512:1024] if net.max_mean_concat else None
         prec = net.precision if not net.max_mean_concat else "fp32"
         ops.pointnet_encode_forward(x, N, C, self.enc_params(), net.act_name, prec, feat[:, :512], fmean,
-                                    buf["argmax"], buf["h2mean"])
+                                    buf["argmax"] if (need_backward or net.max_mean_concat) else None, buf["h2mean"])
         if p:
             ops.copy_rows(x[:, N * C:N * C + p], feat[:, net.feat_dim - p:])
         f = net.final_mlp
@@ -268,7 +269,7 @@ class _Conv3DRunner(_Runner):
         e = self.net.encoder
         return [e.conv1, e.conv2, e.conv3]
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, need_backward: bool = True) -> torch.Tensor:
         net, prec = self.net, self.net.precision
         B = x.shape[0]
         buf = self._get(B, x.device)
