@@ -19,6 +19,20 @@ int32_t* pm_tc_sticky_word() {
   return g_sticky[dev];
 }
 
+// SMs of the current device (cached per device).  Grids and workspaces are SIZED for PM_NUM_SMS = 148 (B200); kernels whose
+// correctness depends on co-residency (the grid barrier of pm_fused_step) additionally cap their grid at the real count.
+int pm_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PM_NUM_SMS;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = PM_NUM_SMS;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 extern "C" {
 // first protocol error any tcgen05 kernel reported on the current device since the last clear (0 = none); synchronises the device
 int pm_tc_sticky_error(int clear) {

@@ -30,7 +30,7 @@ static inline int pm_cdiv(long long a, long long b) { return (int)((a + b - 1) /
 static inline size_t pm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline bool pm_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
-constexpr int PM_NUM_SMS = 148;
+constexpr int PM_NUM_SMS = 148;      // B200; sizing constant for grids / workspaces (pm_sm_count() in api.cu is the runtime value)
 
 // ---------------------------------------------------------------- activations (network.py:7-24)
 __device__ __forceinline__ float pm_act_fwd(int act, float x) {

@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 int32_t* pm_tc_sticky_word();
+int pm_sm_count();
 
 namespace {
 
@@ -227,6 +228,8 @@ fused_step_kernel(const FusedStepP p) {
 inline int fs_grid(int64_t total) {
   int g = (int)((total + 4 * FS_THREADS - 1) / (4 * FS_THREADS));
   if (g > PM_NUM_SMS) g = PM_NUM_SMS;
+  const int sms = pm_sm_count();                 // the grid barrier needs every CTA resident at once
+  if (g > sms) g = sms;
   if (g < 1) g = 1;
   return g;
 }
