@@ -29,7 +29,9 @@ constexpr int BT_THREADS = 256;          // 8 warps, thread = (row, column half)
 // Measured alternatives (scripts/bwd_timing.py): 16 compute warps + an MMA warp (96-register cap) spills the dW3
 // accumulators to local memory and runs 30 % slower; a dedicated issuer warp does not help either, because the M3/M2 operand
 // streams (8 KB of SMEM per 64-cycle MMA) saturate shared memory and the column sums that run beside them slow down equally;
-// M2 as 8 N=256 MMAs (dW2 transposed, both operands MN-major) is correct but slower too (0.468 vs 0.427 ms).
+// M2 as 8 N=256 MMAs (dW2 transposed, both operands MN-major) is correct but slower too (0.468 vs 0.427 ms); round 2: 16 warps with
+// thread = (row, column QUARTER) at the 128-register cap (88 B of spills) is correct and slower as well (0.463 ms) — the epilogues are
+// bound by MUFU.TANH (16/clk) and the shared-memory reads of W3 / H1, not by issue slots.
 constexpr int NCB = 8;                   // channel blocks of 64
 constexpr uint32_t KB16 = 16384;         // one 64-wide k-block of a 128-row operand
 constexpr uint32_t KB32 = 32768;         // one 64-wide k-block of a 256-row operand
