@@ -468,6 +468,21 @@ def main():
         except Exception as e:  # pragma: no cover - keep the headline line alive
             configs["dagger_2048x2048"] = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
+        # ---- BASELINE config 5's stand-in on one GPU: the `depth_sparse` observation (1024 band voxels x (x, y, z, tsdf)) into
+        #      PointNet with C = 4, bf16 (the reference has no Sparse-UNet: SURVEY H4)
+        try:
+            env4 = FakeVecEnv(E, N_PTS * 4, ACT, dev, cloud=True, channels=4, pool=8, seed=99)
+            net4 = dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, point_num=N_PTS, precision="bf16")
+            r4 = ppo(env4, ppo_cfg(E, dev, "bf16", net=net4), _Logger())
+            ms4, _, _ = timed(r4, env4, 3, 3, False)
+            configs["config5_standin_pointnet_c4"] = {
+                "value": E * T_STEPS / (ms4 * 1e-3), "unit": "env*steps/s", "ms_per_step": ms4, "steps": 3, "warmup": 3, "dtype": "bf16",
+                "workload": f"ppo, {E} envs x {N_PTS} sparse voxels x 4 ch (x, y, z, tsdf) into PointNet (C = 4), one GPU of config 5's 8"}
+            r4.release_graph()
+            del env4, r4
+        except Exception as e:  # pragma: no cover
+            configs["config5_standin_pointnet_c4"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
         # ---- the shipped state policy: ppo + MLP 53 -> 512^3 -> 10 at E = 2048 (cfg/algos/ppo.yaml)
         try:
             configs["state_mlp_2048"] = bench_state_mlp(dev, peak_tf, peak_src, kernel_ms)

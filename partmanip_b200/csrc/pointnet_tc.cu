@@ -20,6 +20,8 @@
 //                      symmetric max-pool a per-thread FMNMX3 tree over TMEM columns; the argmax rides in the low 4 mantissa
 //                      bits of the compared value; the two column halves are merged once per cloud.
 // TMEM/b2/x loads are software-pipelined one step ahead.  Per-role clock64 stamps: make EXTRA=-DPM_TC_TIMING + scripts/tc_timing.py.
+// Round-2 experiments that did NOT help (both parity-green): groups A alone running the layer-2 epilogue (0.517 ms, same: the epilogue is
+// MUFU-bound whoever runs it), and half of the next tile's layer 1 computed inside the accumulator wait (0.552 ms, slower).
 // The (points x 128/256/512) activations never leave the SM; HBM sees 4C bytes per point in and 4 KB per cloud out.
 #include "tc_common.cuh"
 
