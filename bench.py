@@ -374,8 +374,8 @@ def main():
         rows = B * 512
         roof = {"bound": "tensor", "kernel": "pointnet encoder forward (%s), %d clouds x %d pts per launch" % (prec, B, N_PTS),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src,
-                "traffic": 25571072 if (prec == "bf16" and B == 2048) else None,
-                "traffic_source": "ncu --set full capture committed under profiles/ (dram__bytes_read.sum + write.sum of one launch); "
+                "traffic": 25563136 if (prec == "bf16" and B == 2048) else None,
+                "traffic_source": "profiles/r02z_encoder_fwd_tc_ncu_metrics.txt: ncu --set full capture (dram__bytes_read.sum + write.sum of one launch); "
                                   "not measured live by bench.py" if (prec == "bf16" and B == 2048) else None,
                 "algorithmic_bytes": B * N_PTS * CH * 4, "algorithmic_flops": B * ENC_FLOPS_PER_CLOUD,
                 "ms_per_launch": enc_ms, "share_of_step": enc_ms * fwd_per_iter / ms_step,

@@ -93,3 +93,57 @@ def test_conv3d_patch_gather_and_its_adjoint():
         rhs = float((xcl.reshape(-1, Cin).double() * din.double()).sum())
         scale = float(cols[:, :K].double().norm() * g[:, :K].double().norm())      # din is summed in fp32: error ~1e-7 of this scale
         assert abs(lhs - rhs) <= 1e-5 * scale, (Cin, k, s, lhs, rhs, scale)
+
+
+def test_dagger_update_with_the_conv3d_student_vs_oracle(tmp_path):
+    """What dagger_tsdf.yaml ships: a Conv3DNet student on TSDF volumes (+ proprio tail) imitating a frozen state teacher.  One DAgger
+    update step (dagger.py:299-337) through the `dagger` plugin against the numpy Conv3D oracle + the restated Adam step: loss and
+    every updated student tensor."""
+    from oracle import ppo_oracle as O
+    from partmanip_b200.algorithms import dagger
+    from partmanip_b200.envs import FakeVecEnv
+    torch.manual_seed(2)
+    E, A, Dt, p, R = 4, 10, 53, 7, 50
+    D = R ** 3 + p
+    g = torch.Generator().manual_seed(21)
+    tea_cfg = dict(action_std=0.5, action_activate="tanh", clipAction=1.0, network=dict(name="MLP", hid_dim=[64, 64], activation="elu"))
+    tea_p = O.mlp_init(Dt, A, [64, 64], gen=g)
+    tea_sd = {f"actor.{k}": v for k, v in tea_p.items()}
+    tea_sd.update({f"critic.{k}": v for k, v in O.mlp_init(Dt, 1, [64, 64], gen=g).items()})
+    tea_sd["log_std"] = torch.full((A,), -0.69)
+    path = str(tmp_path / "teacher.pth")
+    torch.save(dict(obs_mode="state", model_cfg=tea_cfg, model_state_dict=tea_sd, tricks=dict(use_state_norm=False)), path)
+
+    class _Logger:
+        save_ckpt_dir = save_video_dir = save_pose_dir = str(tmp_path)
+
+        def info(self, d, it):
+            pass
+    cfg = dict(num_envs=E, obs_mode="obs", max_iterations=10, n_steps=4, n_updates=1, n_minibatches=1, device=DEV, buf_size=4,
+               reward_reset=False, add_proprio_obs=True, offline_data_pth=None, eval_round=1, eval_frequence=10 ** 9, save_frequence=10 ** 9,
+               test_only=False, save_pose=False, save_video=False, lr_schedule="fixed", lr=1e-4, teacher=path, resume=None, pretrain=None,
+               sampler="sequential", model=dict(action_std=0.1, action_activate="tanh", clipAction=1.0,
+                                                network=dict(name="Conv3DNet", activation="tanh")))
+    env = FakeVecEnv(E, D, A, DEV, cloud=False, seed=5, extra_obs={"state": Dt, "proprio_state": p})
+    r = dagger(env, cfg, _Logger())
+    assert type(r.student.actor).__name__ == "Conv3DNet" and r.student.actor.proprio_shape == p and r.student.actor.res == R
+    w0 = {k[len("actor."):]: v.detach().cpu().numpy().copy() for k, v in r.student.state_dict().items() if k.startswith("actor.")}
+    stu_obs, tea_obs = r._reset_env()
+    stu_obs, tea_obs, _ = r._collect(stu_obs, tea_obs)
+    S, Tt = r.storage.observations[:16].cpu(), r.storage.tea_obs[:16].cpu()
+    r.update(1)
+    # ---- oracle: loss = mean((tea_act - tanh(mu))^2), d/dmu, Conv3D backward, Adam step 1
+    tea_act = O.action_activation(O.mlp_forward(tea_p, Tt, "elu"), 1.0).numpy()
+    mu, _ = C.conv3dnet_forward(S.numpy(), w0, "tanh", p, keep=True)
+    t = np.tanh(mu)
+    loss = float(((tea_act - t) ** 2).mean())
+    gy = (2.0 * (t - tea_act) * (1 - t * t) / t.size).astype(np.float32)
+    _, grads = C.conv3dnet_backward(S.numpy(), w0, "tanh", p, gy)
+    assert abs(r.log_dict["Train/dagger_loss"] - loss) <= 1e-4 * max(1.0, abs(loss)), (r.log_dict["Train/dagger_loss"], loss)
+    opt = O.AdamState({k: torch.from_numpy(v.copy()) for k, v in w0.items()}, 1e-4)
+    opt.apply({k: torch.from_numpy(v) for k, v in grads.items()})
+    got = {k[len("actor."):]: v.detach().cpu() for k, v in r.student.state_dict().items() if k.startswith("actor.")}
+    for k, v in opt.params.items():
+        d = (got[k] - v).abs()
+        # Adam's first step moves every weight by ~lr * sign(g): elements whose gradient is within rounding of 0 may differ by up to 2 lr
+        assert float((d > 0.05 * 1e-4).float().mean()) <= 0.02 and float(d.max()) <= 2.1e-4, (k, float((d > 5e-6).float().mean()), float(d.max()))
