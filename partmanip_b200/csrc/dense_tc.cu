@@ -357,8 +357,9 @@ int pm_linear_forward_tc(const float* x, int64_t ldx, const float* W, const floa
   return PM_OK;
 }
 
+constexpr int DB_SPLITS_MAX = 8 * PM_NUM_SMS;
 size_t pm_linear_backward_tc_ws_bytes(int M, int N, int K) {
-  return (size_t)dw_splits_tc(M, N, K) * ((size_t)N * K + N) * sizeof(float) + 256;
+  return ((size_t)dw_splits_tc(M, N, K) * (size_t)N * K + (size_t)DB_SPLITS_MAX * N) * sizeof(float) + 256;
 }
 
 int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const float* dpre, int64_t lddpre, float* dW, float* db,
@@ -374,6 +375,7 @@ int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const flo
   const int kps = pm_cdiv(pm_cdiv(M, splits), TBK) * TBK;
   float* part = reinterpret_cast<float*>(ws);
   float* dbpart = part + (size_t)splits * N * K;
+  const size_t ws_db_floats = (size_t)DB_SPLITS_MAX * N;
   {
     GemmTcP p{};
     p.A = dpre; p.lda = lddpre; p.a_mn = 1;         // A[K=rows x M=N'] : dpre as stored
@@ -384,8 +386,15 @@ int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const flo
     if (rc) return rc;
     splitk_reduce_tc_kernel<<<pm_cdiv((int64_t)N * K, 256), 256, 0, st>>>(part, splits, (int64_t)N * K, dW);
     if (db) {
-      colsum_split_kernel<<<dim3(pm_cdiv(N, 128), splits), 256, 0, st>>>(dpre, lddpre, M, N, m_dev, kps, dbpart);
-      splitk_reduce_tc_kernel<<<pm_cdiv(N, 256), 256, 0, st>>>(dbpart, splits, N, db);
+      // the column sums get their own (finer) split: the rows are streamed once and the kernel lives on loads in flight
+      int csplits = pm_cdiv(8 * PM_NUM_SMS, pm_cdiv(N, 128));
+      const int cmax = (int)((ws_db_floats) / (size_t)N);
+      if (csplits > cmax) csplits = cmax;
+      if (csplits > pm_cdiv(M, 64)) csplits = pm_cdiv(M, 64);
+      if (csplits < 1) csplits = 1;
+      const int crows = pm_cdiv(pm_cdiv(M, csplits), TBK) * TBK;
+      colsum_split_kernel<<<dim3(pm_cdiv(N, 128), csplits), 256, 0, st>>>(dpre, lddpre, M, N, m_dev, crows, dbpart);
+      splitk_reduce_tc_kernel<<<pm_cdiv(N, 256), 256, 0, st>>>(dbpart, csplits, N, db);
     }
   }
   // ---- dx[M,K] = (dpre W) * act'(x)
