@@ -19,6 +19,8 @@
 // CTA's 256 threads convert and store stage s^1 and already hold the global loads of the block after that in registers.
 #include "tc_common.cuh"
 
+int pm_sm_count();                               // api.cu
+
 namespace {
 using namespace pmtc;
 
@@ -128,7 +130,7 @@ gemm_tc_kernel(const GemmTcP p) {
   using Plan = SmemPlan<PARTS>;
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;      // M tiles on grid.x (up to 2^31-1; a conv layer has 10^7 patch rows)
+  const int n0 = blockIdx.y * TBN;
   int M = p.M, K = p.K;
   int k_begin = 0, k_end = K;
   if (EPI == EPI_DW) {
@@ -141,8 +143,10 @@ gemm_tc_kernel(const GemmTcP p) {
     k_end = min(K, k_begin + kps);
   } else {
     if (p.lim_dev) M = min(M, *p.lim_dev);
-    if (m0 >= M) return;                         // uniform per CTA: before any barrier / TMEM allocation
+    if ((int)blockIdx.x * TBM >= M) return;      // uniform per CTA: before any barrier / TMEM allocation
   }
+  // M tiles are dealt round-robin to the CTAs of a column (FWD / DX launch at most two CTAs per SM and walk the tiles; DW has one)
+  const int n_mtiles = (M + TBM - 1) / TBM;
   const int nkb = (k_end - k_begin + TBK - 1) / TBK;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Plan::BAR + 32);
   constexpr int NSTG = Plan::NSTG;
@@ -166,13 +170,20 @@ gemm_tc_kernel(const GemmTcP p) {
 
   TileRegs ra, rb;
   if (nkb > 0) {
-    load_tile<A_MN>(ra, p.A, p.lda, m0, k_begin, M, k_end, tid);
+    load_tile<A_MN>(ra, p.A, p.lda, (int)blockIdx.x * TBM, k_begin, M, k_end, tid);
     load_tile<B_MN>(rb, p.B, p.ldb, n0, k_begin, p.N, k_end, tid);
   }
+  uint32_t uses[NSTG];                           // commits issued so far on each stage barrier (uniform across the CTA)
+#pragma unroll
+  for (int i = 0; i < NSTG; ++i) uses[i] = 0;
+  uint32_t tiles_done = 0;
+  for (int mt = blockIdx.x; mt < n_mtiles && ok; mt += gridDim.x) {
+  const int m0 = mt * TBM;
+  const int mt_next = mt + (int)gridDim.x;
   for (int kb = 0; kb < nkb && ok; ++kb) {
     const int s = kb % NSTG;
-    if (kb >= NSTG) {                            // the MMAs that read this stage NSTG blocks ago are done
-      ok = mbar_wait(bar(s), ((kb / NSTG) - 1) & 1, p.err, 911);
+    if (uses[s] > 0) {                           // the MMAs that last read this stage are done
+      ok = mbar_wait(bar(s), (uses[s] - 1) & 1, p.err, 911);
       if (!ok) break;
     }
     uint8_t* st = smem + s * Plan::STAGE;
@@ -181,6 +192,9 @@ gemm_tc_kernel(const GemmTcP p) {
     if (kb + 1 < nkb) {                          // next block's global loads fly during the barrier and the MMA issue
       load_tile<A_MN>(ra, p.A, p.lda, m0, k_begin + (kb + 1) * TBK, M, k_end, tid);
       load_tile<B_MN>(rb, p.B, p.ldb, n0, k_begin + (kb + 1) * TBK, p.N, k_end, tid);
+    } else if (mt_next < n_mtiles) {             // ... or the NEXT tile's first block: in flight across this tile's MMAs and epilogue
+      load_tile<A_MN>(ra, p.A, p.lda, mt_next * TBM, k_begin, M, k_end, tid);
+      load_tile<B_MN>(rb, p.B, p.ldb, n0, k_begin, p.N, k_end, tid);
     }
     fence_proxy_async();
     __syncthreads();
@@ -204,9 +218,11 @@ gemm_tc_kernel(const GemmTcP p) {
       umma_commit_1cta(bar(s));                  // frees the stage when these MMAs have read it
       if (kb == nkb - 1) umma_commit_1cta(bar(NSTG));
     }
+    ++uses[s];
     __syncwarp();
   }
-  if (ok && nkb > 0) ok = mbar_wait(bar(NSTG), 0, p.err, 912);
+  if (ok && nkb > 0) ok = mbar_wait(bar(NSTG), tiles_done & 1, p.err, 912);
+  ++tiles_done;
   if (ok) {
     tc_fence_after();
     // ---- epilogue: warp w reads TMEM lanes (w & 3) * 32 .. +32 (rows), columns (w >> 2) * 64 .. +64
@@ -216,20 +232,19 @@ gemm_tc_kernel(const GemmTcP p) {
     float* C = p.C;
     if (EPI == EPI_DW) C += (int64_t)blockIdx.z * p.M * p.ldc;
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      uint32_t v[32];
+    for (int cc = 0; cc < 4; ++cc) {             // 16 columns at a time: the next tile's prefetched operands (64 registers) stay live
+      uint32_t v[16];
       if (nkb > 0) {
-        tmem_ld32(taddr + cc * 32, v);
+        tmem_ld16(taddr + cc * 16, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0u;
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
       }
-      const int col0 = n0 + half * 64 + cc * 32;
+      const int col0 = n0 + half * 64 + cc * 16;
       if (row < M) {
-        float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           float x = __uint_as_float(v[i]);
           const int col = col0 + i;
           if (col < p.N) {
@@ -240,21 +255,23 @@ gemm_tc_kernel(const GemmTcP p) {
               if (p.act != PM_ACT_NONE) x *= pm_act_bwd(p.act, __ldg(p.aux + (int64_t)row * p.ldaux + col));
             }
           }
-          o[i] = x;
+          v[i] = __float_as_uint(x);
         }
         float* dst = C + (int64_t)row * p.ldc + col0;
-        if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        if (col0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            reinterpret_cast<float4*>(dst)[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) dst[i] = o[i];
+          for (int i = 0; i < 16; ++i)
+            if (col0 + i < p.N) dst[i] = __uint_as_float(v[i]);
         }
       }
     }
+    tc_fence_before();                           // the next tile's first MMA overwrites the accumulator: ordered by the next __syncthreads
   }
+  }  // tiles
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -321,6 +338,15 @@ inline int dw_splits_tc(int Mrows, int N, int K) {
   return s;
 }
 
+// FWD / DX: CTAs of an output column walk the M tiles round-robin; enough CTAs to fill the SMs at the kernel's occupancy
+// (__launch_bounds__(.., 2)), never more than there are tiles
+inline int gemm_tc_grid_x(int M, int n_tiles_n) {
+  const int m_tiles = pm_cdiv(M, TBM);
+  int gx = pm_cdiv(2 * pm_sm_count(), n_tiles_n);
+  if (gx > m_tiles) gx = m_tiles;
+  return gx < 1 ? 1 : gx;
+}
+
 template <int PARTS, int EPI, bool A_MN, bool B_MN>
 int launch_gemm_tc(const GemmTcP& p, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
@@ -349,7 +375,7 @@ int pm_linear_forward_tc(const float* x, int64_t ldx, const float* W, const floa
   p.B = W; p.ldb = K; p.b_mn = 0;
   p.C = y; p.ldc = ldy; p.M = M; p.N = N; p.K = K; p.bias = b; p.act = act; p.lim_dev = m_dev;
   p.err = ErrSink{nullptr, pm_tc_sticky_word()};
-  const dim3 grid(pm_cdiv(M, TBM), pm_cdiv(N, TBN), 1);
+  const dim3 grid(gemm_tc_grid_x(M, pm_cdiv(N, TBN)), pm_cdiv(N, TBN), 1);
   int rc = precision == PM_PREC_BF16 ? launch_gemm_tc<1, EPI_FWD, false, false>(p, grid, pm_st(s))
                                      : launch_gemm_tc<3, EPI_FWD, false, false>(p, grid, pm_st(s));
   if (rc) return rc;
@@ -403,7 +429,7 @@ int pm_linear_backward_tc(const float* x, int64_t ldx, const float* W, const flo
     q.A = dpre; q.lda = lddpre; q.a_mn = 0;
     q.B = W; q.ldb = K; q.b_mn = 1;                 // B[K=N' x N=K'] : W as stored
     q.C = dx; q.ldc = lddx; q.M = M; q.N = K; q.K = N; q.act = act_prev; q.aux = x; q.ldaux = ldx; q.lim_dev = m_dev; q.err = sink;
-    const dim3 grid(pm_cdiv(M, TBM), pm_cdiv(K, TBN), 1);
+    const dim3 grid(gemm_tc_grid_x(M, pm_cdiv(K, TBN)), pm_cdiv(K, TBN), 1);
     int rc = precision == PM_PREC_BF16 ? launch_gemm_tc<1, EPI_DX, false, true>(q, grid, st) : launch_gemm_tc<3, EPI_DX, false, true>(q, grid, st);
     if (rc) return rc;
   }

@@ -17,7 +17,8 @@ def cu(t):
 
 
 SHAPES = [(9, 96, 37, "tanh"), (2048, 512, 53, "tanh"), (2048, 512, 512, "tanh"), (300, 10, 512, None), (129, 1, 512, "elu"),
-          (1000, 256, 128, "relu"), (1, 7, 5, "tanh"), (257, 130, 200, "elu")]
+          (1000, 256, 128, "relu"), (1, 7, 5, "tanh"), (257, 130, 200, "elu"),
+          (100001, 256, 128, "tanh"), (77777, 128, 256, "relu")]   # ~5 and ~2 M tiles per CTA: the round-robin tile walk
 
 
 @pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("bf16", 1e-2)])
@@ -107,3 +108,18 @@ def test_mlp_reference_recordings(name, D, out, hid, act, precision, rtol):
         got = dict(net.named_parameters())[k].grad.cpu()
         tol = (rtol if precision != "bf16" else 3e-2) * float(v.abs().max()) + 1e-6
         assert float((got - v).abs().max()) <= tol, (k, float((got - v).abs().max()), tol)
+
+
+def test_tc_device_row_limit_many_tiles():
+    """Device-side row limit with more M tiles than resident CTAs: every CTA walks several tiles, the walk stops at the limit."""
+    from partmanip_b200 import ops
+    torch.manual_seed(2)
+    M, N, K, live = 90000, 128, 64, 61111
+    x, W, b = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N)
+    x[live:] = float("nan")
+    lim = torch.tensor([live], dtype=torch.int32, device=DEV)
+    out = torch.full((M, N), -7.0, device=DEV)
+    ops.linear_forward_tc(cu(x), cu(W), cu(b), "tanh", "fp32", out=out, m_dev=lim)
+    want = torch.tanh(x[:live].double() @ W.double().T + b.double()).float()
+    assert float((out[:live].cpu() - want).abs().max()) <= 1e-4
+    assert bool((out[live:] == -7.0).all())
