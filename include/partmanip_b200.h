@@ -379,6 +379,47 @@ int pm_mesh2sdf_query(const float* sdf_field, int64_t field_stride, const int32_
                       int M, int bbox_res_y, int bbox_res_z, const float* pose_R, const float* pose_T, const float* init_tsdf, int E,
                       int resolution, const float* vox_origin, float size, float* out, pm_stream_t st);
 
+/* ------------------------------------------------------------------------------------------
+ * NEXT ROW (second half): the env-side arithmetic of the open_drawer task around the physics step, one launch
+ * per phase.  The simulator's flat state tensors are read IN PLACE through the task's own int64 index tables
+ * (dof_state_mask (E, num_dofs + 1), rigid_body_mask (E, num_rigid_body + 2): tasks/open_drawer.py:58-70).
+ *
+ * pm_open_drawer_post_physics replaces tasks/open_drawer.py:240-281 (compute_observations, with franka.update_state
+ *   tasks/load_robot.py:153-164) when do_obs, tasks/open_drawer.py:170-238 (compute_reward) when do_reward, and
+ *   `progress_buf += 1` (tasks/hand_base.py:388) when advance_progress.  obs (E, 29 + 2 num_dofs) = the `normal_state` row;
+ *   extras_f (6, E) = reaching_reward, close_reward, rot_reward, joint_state_reward, is_grasped, step_id;
+ *   extras_b (3, E) = is_open, is_open_notgrasp, is_reached;  raw_reward aliases rew_buf as in the reference.
+ * pm_franka_control replaces tasks/load_robot.py:96-118 (franka.control, driveMode 'pos' / 'ik', fixed or mobile base) and
+ *   :142-151 (solve_ik: damped least squares on the mean of the two finger-tip Jacobians; the 6x6 system is solved by Cholesky
+ *   instead of torch.inverse).  Joint positions: dof_state_mask != null -> qpos = the simulator's dof_state_all, read through the
+ *   index table (mask_ld wide); dof_state_mask == null -> a strided view q[e, j] = qpos[e * qpos_row_stride + j * qpos_elem_stride]
+ *   (franka.dof_qpos_raw as update_state leaves it).  jacobian (E, n_links, 6, num_dofs); default_root_quat: HOST array of 4 (x, y, z, w);
+ *   jacobian_sum (device scalar or null) receives sum(j_eef), the value the reference tests against 1e-5 before exit(1).
+ * pm_episode_flags replaces tasks/hand_base.py:367-377: train != 0 updates epis_max_step / epis_max_rew, writes reset_buf,
+ *   reset_succ and succ_rate = sum(success) / max(sum(reset_buf), 1); train == 0 writes reset_buf = progress >= max_episode_length.
+ *   counts3 (3 x int32, device): [0] = sum(success), [1] = sum(reset_buf) (the value `if self.reset_buf.sum() > 0` reads), [2] scratch.
+ * pm_scatter_dof_targets replaces tasks/hand_base.py:382: pos_act_all[dof_state_mask[:, :num_dofs]] = pos_act.
+ * ------------------------------------------------------------------------------------------ */
+enum { PM_DRIVE_POS = 0, PM_DRIVE_IK = 1 };
+int pm_open_drawer_obs_dim(int num_dofs);
+int pm_open_drawer_post_physics(const float* dof_state_all, const float* rigid_body_all, const float* root_tensor, int n_actors,
+                                int obj_actor, const int64_t* dof_state_mask, const int64_t* rigid_body_mask, int E, int num_dofs,
+                                int num_rigid_body, int ltip_rb_index, int rtip_rb_index, const float* dof_lower, const float* dof_upper,
+                                const float* part_bbox_init, const float* part_axis_dir_init, const float* part_joint_lower,
+                                const float* part_joint_upper, const int64_t* obj_lstid, float suc_prop, int do_obs, int do_reward,
+                                int advance_progress, int64_t* progress_buf, float* obs, float* part_bbox, float* dof_state,
+                                float* rigid_body, float* tip_rb, float* tip_rot_9d, float* gripper_length, float* dof_qpos_normalized,
+                                float* rew_buf, uint8_t* success, uint8_t* succ_objid, float* extras_f, uint8_t* extras_b, pm_stream_t s);
+int pm_franka_control(const float* raw_output, int E, int num_dofs, int mobile, int drive_mode, const float* qpos, int64_t qpos_row_stride,
+                      int64_t qpos_elem_stride, const int64_t* dof_state_mask, int mask_ld, const float* jacobian, int n_links, int ltip_rb_index,
+                      int rtip_rb_index, const float* dof_lower, const float* dof_upper, const float* default_root_quat, float dt,
+                      float damping, float* action_tensor, float* jacobian_sum, pm_stream_t s);
+int pm_episode_flags(int E, int train, const float* rew_buf, const int64_t* progress_buf, const uint8_t* success, float* epis_max_rew,
+                     int64_t* epis_max_step, int64_t explore_step, int64_t max_episode_length, uint8_t* reset_buf, uint8_t* reset_succ,
+                     int32_t* counts3, float* succ_rate, pm_stream_t s);
+int pm_scatter_dof_targets(const float* pos_act, const int64_t* dof_state_mask, int mask_ld, int E, int num_dofs, float* pos_act_all,
+                           pm_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

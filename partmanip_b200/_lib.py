@@ -88,6 +88,12 @@ SIGNATURES = {
     "pm_conv3d_first_backward_ws_bytes": (SZ, []),
     "pm_conv3d_first_backward": (I, [P, L, I, I, P, P, P, P]),
     "pm_mesh2sdf_query": (I, [P, L, P, P, P, I, I, I, P, P, P, I, I, C.POINTER(F), F, P, P]),
+    "pm_open_drawer_obs_dim": (I, [I]),
+    "pm_open_drawer_post_physics": (I, [P, P, P, I, I, P, P, I, I, I, I, I, P, P, P, P, P, P, P, F, I, I, I, P,
+                                        P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "pm_franka_control": (I, [P, I, I, I, I, P, L, L, P, I, P, I, I, I, P, P, C.POINTER(F), F, F, P, P, P]),
+    "pm_episode_flags": (I, [I, I, P, P, P, P, P, L, L, P, P, P, P, P]),
+    "pm_scatter_dof_targets": (I, [P, P, I, I, I, P, P]),
     "pm_gather_rows": (I, [P, L, P, P, L, L, I, P]),
     "pm_copy_rows": (I, [P, L, P, L, L, I, P]),
 }

@@ -656,3 +656,104 @@ def farthest_point_sample(points: Tensor, K: int, return_idx: bool = False, comp
     check(lib.pm_farthest_point_sample(_p(points), E, P, int(K), int(compact), _p(out), _p(idx), _p(ws), nbytes, _stream()),
           "pm_farthest_point_sample")
     return (out, idx) if return_idx else out
+
+
+# ------------------------------------------------------------------------------------------- next row: env-side arithmetic (open_drawer)
+def _i64(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda or t.dtype != torch.int64 or not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous CUDA int64 tensor")
+    return t
+
+
+class OpenDrawerPostPlan:
+    """tasks/open_drawer.py:240-281 + 170-238 (+ load_robot.py:153-164, hand_base.py:388) in ONE launch.  The simulator tensors,
+    index tables and result buffers are persistent, so the arguments are validated and converted once; a call costs one ctypes
+    dispatch.  `out` holds the preallocated result tensors (see tasks/open_drawer_step.py:_pm_buffers)."""
+
+    def __init__(self, dof_state_all: Tensor, rigid_body_all: Tensor, root_tensor: Tensor, obj_actor: int, dof_state_mask: Tensor,
+                 rigid_body_mask: Tensor, ltip_rb_index: int, rtip_rb_index: int, dof_lower: Tensor, dof_upper: Tensor, part_bbox_init: Tensor,
+                 part_axis_dir_init: Tensor, part_joint_lower: Tensor, part_joint_upper: Tensor, obj_lstid: Tensor, suc_prop: float,
+                 progress_buf: Tensor, succ_objid: Tensor, out: dict):
+        E, ndp = dof_state_mask.shape
+        nd, nb = ndp - 1, rigid_body_mask.shape[1] - 2
+        _i64(dof_state_mask, "dof_state_mask"), _i64(rigid_body_mask, "rigid_body_mask"), _i64(obj_lstid, "obj_lstid"), _i64(progress_buf, "progress_buf")
+        for n, t in (("dof_state_all", dof_state_all), ("rigid_body_all", rigid_body_all), ("root_tensor", root_tensor), ("dof_lower", dof_lower),
+                     ("dof_upper", dof_upper), ("part_bbox_init", part_bbox_init), ("part_axis_dir_init", part_axis_dir_init),
+                     ("part_joint_lower", part_joint_lower), ("part_joint_upper", part_joint_upper)):
+            assert _f32(t, n).is_contiguous(), n
+        assert dof_state_all.shape[-1] == 2 and rigid_body_all.shape[-1] == 13 and root_tensor.shape[0] == E and root_tensor.shape[-1] == 13
+        assert part_bbox_init.shape == (E, 8, 3) and part_axis_dir_init.numel() == 3 * E and part_joint_lower.numel() == E and part_joint_upper.numel() == E
+        assert dof_lower.numel() == nd and dof_upper.numel() == nd and succ_objid.dtype in (torch.bool, torch.uint8) and succ_objid.is_cuda
+        assert int(dof_state_mask.max()) < dof_state_all.shape[0] and int(rigid_body_mask.max()) < rigid_body_all.shape[0] and int(dof_state_mask.min()) >= 0
+        assert int(obj_lstid.max()) < succ_objid.numel() and progress_buf.numel() == E
+        shapes = dict(obs=(E, 29 + 2 * nd), part_bbox=(E, 8, 3), dof_state_tensor=(E, nd + 1, 2), rigid_body_tensor=(E, nb + 2, 13), tip_rb_tensor=(E, 13),
+                      tip_rot_9d=(E, 3, 3), gripper_length=(E,), dof_qpos_normalized=(E, nd), rew_buf=(E,), success=(E,), extras_f=(6, E), extras_b=(3, E))
+        for k, shp in shapes.items():
+            t = out[k]
+            assert t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp, k
+            assert t.dtype == (torch.bool if k in ("success", "extras_b") else torch.float32), k
+        self._keep = (dof_state_all, rigid_body_all, root_tensor, dof_state_mask, rigid_body_mask, dof_lower, dof_upper, part_bbox_init, part_axis_dir_init,
+                      part_joint_lower, part_joint_upper, obj_lstid, progress_buf, succ_objid, out)
+        self._head = (_p(dof_state_all), _p(rigid_body_all), _p(root_tensor), root_tensor.shape[1], int(obj_actor), _p(dof_state_mask), _p(rigid_body_mask),
+                      E, nd, nb, int(ltip_rb_index), int(rtip_rb_index), _p(dof_lower), _p(dof_upper), _p(part_bbox_init), _p(part_axis_dir_init),
+                      _p(part_joint_lower), _p(part_joint_upper), _p(obj_lstid), float(suc_prop))
+        self._tail = (_p(progress_buf), _p(out["obs"]), _p(out["part_bbox"]), _p(out["dof_state_tensor"]), _p(out["rigid_body_tensor"]),
+                      _p(out["tip_rb_tensor"]), _p(out["tip_rot_9d"]), _p(out["gripper_length"]), _p(out["dof_qpos_normalized"]), _p(out["rew_buf"]),
+                      _p(out["success"]), _p(succ_objid), _p(out["extras_f"]), _p(out["extras_b"]))
+
+    def __call__(self, do_obs: bool = True, do_reward: bool = True, advance_progress: bool = False) -> None:
+        check(lib.pm_open_drawer_post_physics(*self._head, int(do_obs), int(do_reward), int(advance_progress), *self._tail, _stream()),
+              "pm_open_drawer_post_physics")
+
+
+def franka_control(raw_output: Tensor, drive_mode: str, mobile: bool, qpos: Tensor, num_dofs: int, dof_lower: Tensor, dof_upper: Tensor,
+                   default_root_quat, dt: float, action_tensor: Tensor, dof_state_mask: Optional[Tensor] = None, jacobian: Optional[Tensor] = None,
+                   ltip_rb_index: int = 0, rtip_rb_index: int = 0, jacobian_sum: Optional[Tensor] = None, damping: float = 0.05) -> Tensor:
+    """tasks/load_robot.py:96-118 + 142-151 in one launch -> action_tensor (E, num_dofs), clamped to the joint limits.
+    qpos: the simulator's dof_state_all (with dof_state_mask, the task's index table) or a strided (E, num_dofs) view of the
+    current joint positions (franka.dof_qpos_raw)."""
+    E = raw_output.shape[0]
+    mode = {"pos": 0, "ik": 1}.get(drive_mode)
+    if mode is None:
+        raise NotImplementedError(drive_mode)
+    lo = 3 if mobile else 0
+    assert _f32(raw_output, "raw_output").is_contiguous() and raw_output.shape[1] == (7 if mode else 8) + lo
+    assert _f32(action_tensor, "action_tensor").is_contiguous() and action_tensor.shape == (E, num_dofs)
+    assert _f32(dof_lower, "dof_lower").numel() == num_dofs and _f32(dof_upper, "dof_upper").numel() == num_dofs
+    _f32(qpos, "qpos", last_contig=False)
+    if dof_state_mask is not None:
+        assert qpos.is_contiguous() and qpos.shape[-1] == 2 and _i64(dof_state_mask, "dof_state_mask").shape[0] == E
+        rs, es, mld = 0, 0, dof_state_mask.shape[1]
+    else:
+        assert qpos.shape == (E, num_dofs)
+        rs, es, mld = qpos.stride(0), qpos.stride(1), 0
+    n_links = 0
+    if mode:
+        assert _f32(jacobian, "jacobian").is_contiguous() and jacobian.shape[0] == E and jacobian.shape[2:] == (6, num_dofs)
+        n_links = jacobian.shape[1]
+    quat = (ct.c_float * 4)(*[float(v) for v in default_root_quat]) if mobile else None
+    check(lib.pm_franka_control(_p(raw_output), E, int(num_dofs), int(mobile), mode, _p(qpos), rs, es, _p(dof_state_mask), mld, _p(jacobian), n_links,
+                                int(ltip_rb_index), int(rtip_rb_index), _p(dof_lower), _p(dof_upper), quat, float(dt), float(damping),
+                                _p(action_tensor), _p(jacobian_sum), _stream()), "pm_franka_control")
+    return action_tensor
+
+
+def episode_flags(train: bool, rew_buf: Optional[Tensor], progress_buf: Tensor, success: Optional[Tensor], epis_max_rew: Optional[Tensor],
+                  epis_max_step: Optional[Tensor], explore_step: int, max_episode_length: int, reset_buf: Tensor, reset_succ: Optional[Tensor],
+                  counts: Tensor, succ_rate: Optional[Tensor]) -> None:
+    """tasks/hand_base.py:367-377 in one launch (reset_buf / reset_succ / success: bool or uint8 storage)."""
+    E = progress_buf.shape[0]
+    assert _i64(progress_buf, "progress_buf") is not None and counts.dtype == torch.int32 and counts.numel() >= 3 and counts.is_cuda
+    assert reset_buf.dtype in (torch.bool, torch.uint8) and reset_buf.is_cuda and reset_buf.numel() == E
+    if train:
+        assert _f32(rew_buf, "rew_buf").numel() == E and _f32(epis_max_rew, "epis_max_rew").numel() == E and _i64(epis_max_step, "epis_max_step").numel() == E
+        assert success.dtype in (torch.bool, torch.uint8) and reset_succ.dtype in (torch.bool, torch.uint8) and succ_rate.dtype == torch.float32
+    check(lib.pm_episode_flags(E, int(train), _p(rew_buf), _p(progress_buf), _p(success), _p(epis_max_rew), _p(epis_max_step), int(explore_step),
+                               int(max_episode_length), _p(reset_buf), _p(reset_succ), _p(counts), _p(succ_rate), _stream()), "pm_episode_flags")
+
+
+def scatter_dof_targets(pos_act: Tensor, dof_state_mask: Tensor, num_dofs: int, pos_act_all: Tensor) -> None:
+    """tasks/hand_base.py:382."""
+    assert _f32(pos_act, "pos_act").is_contiguous() and pos_act.shape[1] == num_dofs and _f32(pos_act_all, "pos_act_all").is_contiguous()
+    check(lib.pm_scatter_dof_targets(_p(pos_act), _p(_i64(dof_state_mask, "dof_state_mask")), dof_state_mask.shape[1], pos_act.shape[0], int(num_dofs),
+                                     _p(pos_act_all), _stream()), "pm_scatter_dof_targets")

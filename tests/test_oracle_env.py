@@ -1,0 +1,65 @@
+"""Pins oracle/env_oracle.py against the recordings of the unmodified reference methods (tests/golden/env_open_drawer.npz,
+made by tests/golden/make_golden_env.py): tasks/open_drawer.py:170-281, tasks/load_robot.py:96-164, tasks/hand_base.py:367-377."""
+import torch
+
+from oracle import env_oracle as EO
+from tests.helpers import load_golden
+
+
+def _g():
+    return load_golden("env_open_drawer.npz")
+
+
+def _obs(g):
+    return EO.compute_observations(g["in_dof_all"], g["in_rb_all"], g["in_root"], g["in_dof_mask"], g["in_rb_mask"], 1, g["in_part_bbox_init"],
+                                   g["in_part_axis_dir_init"], int(g["in_num_dofs"]), int(g["in_ltip"]), int(g["in_rtip"]), g["in_dof_lower"],
+                                   g["in_dof_upper"])
+
+
+def test_observations_bit_exact():
+    g = _g()
+    o = _obs(g)
+    assert torch.equal(o["obs"], g["obs"]) and o["obs"].shape[1] == 53
+    assert torch.equal(o["part_bbox"], g["part_bbox"])
+    assert torch.equal(o["dof_state_tensor"], g["dof_state_tensor"]) and torch.equal(o["rigid_body_tensor"], g["rigid_body_tensor"])
+    for k in ("tip_rb_tensor", "tip_rot_9d", "gripper_length", "dof_qpos_normalized", "dof_qpos_raw", "dof_qvel_raw"):
+        assert torch.equal(o["robot"][k], g["robot_" + k]), k
+
+
+def test_reward_bit_exact():
+    g = _g()
+    o = _obs(g)
+    r = EO.compute_reward(o["part_bbox"], o["robot"], o["dof_state_tensor"], g["in_part_joint_lower_limits"], g["in_part_joint_upper_limits"], 0.5,
+                          g["in_obj_lstid"], torch.zeros(int(g["in_num_objs"]), dtype=torch.bool))
+    assert torch.equal(r["rew_buf"], g["rew_buf"])
+    assert torch.equal(r["success"].bool(), g["success"].bool()) and torch.equal(r["succ_objid_lst"], g["succ_objid_lst"])
+    for k in ("is_open", "is_open_notgrasp", "reaching_reward", "close_reward", "rot_reward", "is_reached", "joint_state_reward", "raw_reward", "is_grasped"):
+        assert torch.equal(r[k].float(), g["extras_" + k].float()), k
+    assert 0.05 < float(r["success"].float().mean()) < 0.5 and 0.3 < float(r["is_reached"].float().mean()) < 0.9   # a real mix of cases
+
+
+def test_control_bit_exact():
+    g = _g()
+    o = _obs(g)
+    nd, lt, rt = int(g["in_num_dofs"]), int(g["in_ltip"]), int(g["in_rtip"])
+    root = torch.tensor([0.5, 0.0, 0.05, 0.0, 0.0, 1.0, 0.0])
+    q = o["robot"]["dof_qpos_raw"]
+    a = EO.control(g["actions"], "ik", True, q, 1 / 60, root, g["in_dof_lower"], g["in_dof_upper"], g["in_jac"], lt, rt)
+    assert torch.equal(a, g["action_tensor_ik_mobile"])
+    a = EO.control(g["actions_pos_1"], "pos", True, q, 1 / 60, root, g["in_dof_lower"], g["in_dof_upper"])
+    assert torch.equal(a, g["action_tensor_pos_1"])
+    a = EO.control(g["actions_pos_0"], "pos", False, q[:, 3:], 1 / 60, root, g["in_dof_lower"][3:], g["in_dof_upper"][3:])
+    assert torch.equal(a, g["action_tensor_pos_0"])
+    a = EO.control(g["actions_ik_fixed"], "ik", False, q[:, 3:], 1 / 60, root, g["in_dof_lower"][3:], g["in_dof_upper"][3:],
+                   g["in_jac"][..., 3:].contiguous(), lt, rt)
+    assert torch.equal(a, g["action_tensor_ik_fixed"])
+
+
+def test_episode_flags_bit_exact():
+    g = _g()
+    f = EO.episode_flags("train", g["rew_buf"], g["pre_progress_buf"], g["success"].bool(), g["pre_epis_max_rew"], g["pre_epis_max_step"], 40, 200)
+    assert torch.equal(f["epis_max_step"], g["train_epis_max_step"]) and torch.equal(f["epis_max_rew"], g["train_epis_max_rew"])
+    assert torch.equal(f["reset_buf"], g["train_reset_buf"]) and torch.equal(f["reset_succ"], g["train_reset_succ"])
+    assert torch.equal(f["succ_rate"], g["train_succ_rate"])
+    f = EO.episode_flags("test", g["rew_buf"], g["pre_progress_buf"], g["success"].bool(), f["epis_max_rew"], f["epis_max_step"], 40, 60)
+    assert torch.equal(f["reset_buf"], g["test_reset_buf"])
