@@ -410,6 +410,19 @@ int pm_open_drawer_post_physics(const float* dof_state_all, const float* rigid_b
                                 int advance_progress, int64_t* progress_buf, float* obs, float* part_bbox, float* dof_state,
                                 float* rigid_body, float* tip_rb, float* tip_rot_9d, float* gripper_length, float* dof_qpos_normalized,
                                 float* rew_buf, uint8_t* success, uint8_t* succ_objid, float* extras_f, uint8_t* extras_b, pm_stream_t s);
+/* grasp_cube: replaces tasks/grasp_cube.py:118-138 (compute_observations, incl. utils/torch_jit_utils.py:412-425 deambiguity_rotation and
+ * franka.update_state) when do_obs, tasks/grasp_cube.py:66-115 (compute_reward) when do_reward.  The simulator tensors are regular here:
+ * dof_state (E, dofs_per_env, 2), rigid_body (E, bodies_per_env, 13), root_tensor (E, n_actors, 13).  pose_lower_limit / pose_upper_limit
+ * (7), success_pos (3), obj_default_pos (3): HOST arrays.  obs (E, 19 + 2 num_dofs) = `normal_state`; proprio (E, 7 + 2 num_dofs) or null
+ * = `proprio_state`; extras_f (7, E) = reaching_reward, close_reward, rot_reward, reaching_goal_reward, obj_movement, obj_height, step_id;
+ * extras_b (2, E) = is_reached, obj_up_flag. */
+int pm_grasp_cube_obs_dim(int num_dofs);
+int pm_grasp_cube_post_physics(const float* dof_state, int dofs_per_env, const float* rigid_body, int bodies_per_env, const float* root_tensor,
+                               int n_actors, int obj_actor, int E, int num_dofs, int ltip_rb_index, int rtip_rb_index, const float* dof_lower,
+                               const float* dof_upper, const float* pose_lower_limit, const float* pose_upper_limit, const float* success_pos,
+                               const float* obj_default_pos, float goal_thresh, int do_obs, int do_reward, int advance_progress,
+                               int64_t* progress_buf, float* obs, float* proprio, float* tip_rb, float* tip_rot_9d, float* gripper_length,
+                               float* dof_qpos_normalized, float* rew_buf, uint8_t* success, float* extras_f, uint8_t* extras_b, pm_stream_t s);
 int pm_franka_control(const float* raw_output, int E, int num_dofs, int mobile, int drive_mode, const float* qpos, int64_t qpos_row_stride,
                       int64_t qpos_elem_stride, const int64_t* dof_state_mask, int mask_ld, const float* jacobian, int n_links, int ltip_rb_index,
                       int rtip_rb_index, const float* dof_lower, const float* dof_upper, const float* default_root_quat, float dt,

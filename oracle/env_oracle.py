@@ -148,3 +148,60 @@ def episode_flags(train_test_flag, rew_buf, progress_buf, success, epis_max_rew,
     if train_test_flag == "test":
         return dict(reset_buf=progress_buf >= max_episode_length)
     raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------------------------------------------ grasp_cube
+def mat_diff_rad(m1, m2):
+    """utils/torch_jit_utils.py:406-410."""
+    d = torch.matmul(m1.transpose(-1, -2), m2)
+    return torch.acos(torch.clamp((d[..., 0, 0] + d[..., 1, 1] + d[..., 2, 2] - 1) / 2, -1, 1))
+
+
+def deambiguity_rotation(old_r):
+    """utils/torch_jit_utils.py:412-425.  Note the sign flips index dim 2 of the (N, 24, 3, 2) stack: they negate ROW 0 (first 12
+    candidates) and ROW 1 (candidates 6..17) of both selected columns."""
+    R = quat_to_mat(old_r)
+    ind = torch.tensor([[0, 1], [0, 2], [1, 2], [1, 0], [2, 0], [2, 1]])
+    ind = torch.cat([ind, ind, ind, ind], dim=0)
+    m12 = R[:, :, ind].transpose(-2, -3).clone()
+    m12[:, :12, 0] = -m12[:, :12, 0]
+    m12[:, 6:18, 1] = -m12[:, 6:18, 1]
+    m3 = torch.cross(m12[..., 0], m12[..., 1], dim=-1).unsqueeze(-1)
+    allm = torch.cat([m12, m3], dim=-1)
+    rad = mat_diff_rad(allm, torch.eye(3)[None, None])
+    return allm[torch.arange(allm.shape[0]), rad.argmin(dim=1)]
+
+
+def cube_observations(dof, rb, root, obj_actor, num_dofs, ltip, rtip, dof_lower, dof_upper, pose_lo, pose_hi):
+    """tasks/grasp_cube.py:118-126 (+ :132-135 proprio_state)."""
+    rob = update_state(rb, dof, num_dofs, ltip, rtip, dof_lower, dof_upper)
+    obj = root[:, obj_actor]
+    tip_pose = 2 * (rob["tip_rb_tensor"][:, :7] - pose_lo) / (pose_hi - pose_lo) - 1
+    obj_pos = 2 * (obj[:, :3] - pose_lo[:3]) / (pose_hi[:3] - pose_lo[:3]) - 1
+    obj_pose = torch.cat([obj_pos, deambiguity_rotation(obj[:, 3:7]).reshape(obj.shape[0], -1)], dim=-1)
+    obs = torch.cat([tip_pose, obj_pose, rob["dof_qpos_normalized"], rob["dof_qvel_raw"]], dim=-1)
+    proprio = torch.cat([tip_pose, rob["dof_qpos_normalized"], rob["dof_qvel_raw"]], dim=-1)
+    return dict(obs=obs, proprio=proprio, robot=rob, obj_root=obj)
+
+
+def cube_reward(rob, obj_root, success_pos, goal_thresh, obj_default_pos):
+    """tasks/grasp_cube.py:66-115."""
+    pos = obj_root[:, :3]
+    dist = (rob["tip_rb_tensor"][:, :3] - pos).norm(dim=-1)
+    reached = dist < 0.02
+    gl = rob["gripper_length"]
+    close = (0.1 - gl) * reached + 0.1 * (gl - 0.1) * (~reached)
+    orot = deambiguity_rotation(obj_root[:, 3:7])
+    H = quat_to_mat(rob["tip_rb_tensor"][..., 3:7])
+    down = -H[:, -1, -1]
+    p1 = ((H[:, :, 0] * orot[:, :, 0]).abs() + (H[:, :, 1] * orot[:, :, 1]).abs()).sum(dim=-1)
+    p2 = ((H[:, :, 0] * orot[:, :, 1]).abs() + (H[:, :, 1] * orot[:, :, 0]).abs()).sum(dim=-1)
+    rot = down + torch.max(p1, p2) - 3
+    gdist = (pos - success_pos).norm(dim=-1)
+    goal = torch.max(0.2 - gdist, torch.zeros_like(gdist)) * reached
+    rew = -dist + 0.5 * rot + 5 * close + 20 * goal
+    success = (gdist <= goal_thresh) * reached
+    rew = rew + 3 * success
+    return dict(rew_buf=rew, success=success, reaching_reward=-dist, close_reward=close, rot_reward=rot, is_reached=reached,
+                reaching_goal_reward=goal, obj_movement=(pos - obj_default_pos).norm(dim=-1), raw_reward=rew, obj_height=obj_root[..., 2],
+                obj_up_flag=obj_root[..., 2] > 0.1)

@@ -91,6 +91,9 @@ SIGNATURES = {
     "pm_open_drawer_obs_dim": (I, [I]),
     "pm_open_drawer_post_physics": (I, [P, P, P, I, I, P, P, I, I, I, I, I, P, P, P, P, P, P, P, F, I, I, I, P,
                                         P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "pm_grasp_cube_obs_dim": (I, [I]),
+    "pm_grasp_cube_post_physics": (I, [P, I, P, I, P, I, I, I, I, I, I, P, P, C.POINTER(F), C.POINTER(F), C.POINTER(F), C.POINTER(F), F,
+                                       I, I, I, P, P, P, P, P, P, P, P, P, P, P, P]),
     "pm_franka_control": (I, [P, I, I, I, I, P, L, L, P, I, P, I, I, I, P, P, C.POINTER(F), F, F, P, P, P]),
     "pm_episode_flags": (I, [I, I, P, P, P, P, P, L, L, P, P, P, P, P]),
     "pm_scatter_dof_targets": (I, [P, P, I, I, I, P, P]),

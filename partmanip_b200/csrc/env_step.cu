@@ -240,6 +240,150 @@ open_drawer_post_kernel(const OpenDrawerP p, const int n_env_ctas) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- grasp_cube
+struct GraspCubeP {
+  const float* dof;                              // [E, nd_all, 2] (the simulator's dof tensor viewed per env; robot dofs first)
+  const float* rb;                               // [E, nb, 13]
+  const float* root;                             // [E, n_actors, 13]
+  int E, nd, nd_all, nb, n_actors, obj_actor, ltip, rtip;
+  const float* dof_lower;
+  const float* dof_upper;
+  float pose_lo[7], pose_hi[7];                  // pose_lower_limit / pose_upper_limit (grasp_cube.py:18-21)
+  float success_pos[3], obj_default[3], goal_thresh;
+  int do_obs, do_reward, advance_progress;
+  int64_t* progress;
+  float* obs;                                    // [E, 19 + 2 nd]
+  float* proprio;                                // [E, 7 + 2 nd] or null
+  float* tip_rb;                                 // [E, 13]
+  float* tip_rot;                                // [E, 9]
+  float* gripper;                                // [E]
+  float* qpos_norm;                              // [E, nd]
+  float* rew;
+  uint8_t* success;
+  float* extras_f;                               // [7, E]: reaching, close, rot, reaching_goal, obj_movement, obj_height, step_id
+  uint8_t* extras_b;                             // [2, E]: is_reached, obj_up_flag
+};
+
+// utils/torch_jit_utils.py:412-425 deambiguity_rotation: of the 24 matrices built from ordered column pairs of R with the row
+// sign patterns below (third column = cross product), the one closest to the identity (smallest acos((trace - 1) / 2); first
+// index on ties, torch.argmin).
+__device__ __forceinline__ void deambiguity_rotation(const float* q, float* best /* 9 */) {
+  float R[9];
+  quat_to_mat(q, R);
+  const int ind[6][2] = {{0, 1}, {0, 2}, {1, 2}, {1, 0}, {2, 0}, {2, 1}};
+  float best_rad = 1e30f;
+#pragma unroll 1
+  for (int k = 0; k < 24; ++k) {
+    const int c0 = ind[k % 6][0], c1 = ind[k % 6][1];
+    float a[3] = {R[0 * 3 + c0], R[1 * 3 + c0], R[2 * 3 + c0]};
+    float b[3] = {R[0 * 3 + c1], R[1 * 3 + c1], R[2 * 3 + c1]};
+    if (k < 12) { a[0] = -a[0]; b[0] = -b[0]; }              // all_r_mat_12[:, :12, 0]   : ROW 0 of both columns
+    if (k >= 6 && k < 18) { a[1] = -a[1]; b[1] = -b[1]; }    // all_r_mat_12[:, 6:18, 1]  : ROW 1 of both columns
+    const float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    const float t = (a[0] + b[1] + c[2] - 1) / 2;
+    const float rad = acosf(fminf(fmaxf(t, -1.f), 1.f));
+    if (rad < best_rad) {
+      best_rad = rad;
+      best[0] = a[0]; best[1] = b[0]; best[2] = c[0];
+      best[3] = a[1]; best[4] = b[1]; best[5] = c[1];
+      best[6] = a[2]; best[7] = b[2]; best[8] = c[2];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ENV_THREADS)
+grasp_cube_post_kernel(const GraspCubeP p) {
+  extern __shared__ float s_obs[];
+  const int tid = threadIdx.x;
+  const int e0 = blockIdx.x * ENV_THREADS, e = e0 + tid;
+  const int n_env = min(ENV_THREADS, p.E - e0);
+  const int obs_dim = 19 + 2 * p.nd;
+  if (e < p.E) {
+    const float* lt = p.rb + ((int64_t)e * p.nb + p.ltip) * 13;
+    const float* rt = p.rb + ((int64_t)e * p.nb + p.rtip) * 13;
+    float tip[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) tip[i] = (lt[i] + rt[i]) / 2;
+    const float gl = norm(ld3(lt) - ld3(rt));
+    const float* ro = p.root + ((int64_t)e * p.n_actors + p.obj_actor) * 13;
+    const V3 opos = ld3(ro);
+    float orot[9];
+    deambiguity_rotation(ro + 3, orot);
+    if (p.do_obs) {
+      float* o = s_obs + tid * obs_dim;
+      float* pr = p.proprio ? p.proprio + (int64_t)e * (7 + 2 * p.nd) : nullptr;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {                // grasp_cube.py:122
+        o[i] = 2 * (tip[i] - p.pose_lo[i]) / (p.pose_hi[i] - p.pose_lo[i]) - 1;
+        if (pr) pr[i] = o[i];
+      }
+      o[7] = 2 * (opos.x - p.pose_lo[0]) / (p.pose_hi[0] - p.pose_lo[0]) - 1;
+      o[8] = 2 * (opos.y - p.pose_lo[1]) / (p.pose_hi[1] - p.pose_lo[1]) - 1;
+      o[9] = 2 * (opos.z - p.pose_lo[2]) / (p.pose_hi[2] - p.pose_lo[2]) - 1;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) o[10 + i] = orot[i];
+      for (int j = 0; j < p.nd; ++j) {
+        const float* d = p.dof + ((int64_t)e * p.nd_all + j) * 2;
+        const float qn = 2 * (d[0] - p.dof_lower[j]) / (p.dof_upper[j] - p.dof_lower[j]) - 1;
+        o[19 + j] = qn;
+        o[19 + p.nd + j] = d[1];
+        p.qpos_norm[(int64_t)e * p.nd + j] = qn;
+        if (pr) { pr[7 + j] = qn; pr[7 + p.nd + j] = d[1]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 13; ++i) p.tip_rb[(int64_t)e * 13 + i] = tip[i];
+      float TR[9];
+      quat_to_mat(tip + 3, TR);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) p.tip_rot[(int64_t)e * 9 + i] = TR[i];
+      p.gripper[e] = gl;
+    }
+    int64_t prog = 0;
+    if (p.progress) {
+      prog = p.progress[e];
+      if (p.advance_progress) p.progress[e] = ++prog;
+    }
+    if (p.do_reward) {                             // grasp_cube.py:70-114
+      const float dist = norm(V3{tip[0], tip[1], tip[2]} - opos);
+      const bool reached = dist < 0.02f;
+      const float reaching = -dist;
+      const float close = (0.1f - gl) * (reached ? 1.f : 0.f) + 0.1f * (gl - 0.1f) * (reached ? 0.f : 1.f);
+      float H[9];
+      quat_to_mat(tip + 3, H);
+      const float down = -H[8];
+      float par1 = 0.f, par2 = 0.f;                // sums over the row index of |H[:,0] O[:,0]| + |H[:,1] O[:,1]| (resp. crossed)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        par1 += fabsf(H[r * 3 + 0] * orot[r * 3 + 0]) + fabsf(H[r * 3 + 1] * orot[r * 3 + 1]);
+        par2 += fabsf(H[r * 3 + 0] * orot[r * 3 + 1]) + fabsf(H[r * 3 + 1] * orot[r * 3 + 0]);
+      }
+      const float rot = down + fmaxf(par1, par2) - 3;
+      const float gdist = norm(opos - V3{p.success_pos[0], p.success_pos[1], p.success_pos[2]});
+      const float goal = fmaxf(0.2f - gdist, 0.f) * (reached ? 1.f : 0.f);
+      float rew = reaching + 0.5f * rot + 5 * close + 20 * goal;
+      const bool succ = (gdist <= p.goal_thresh) && reached;
+      rew += 3 * (succ ? 1.f : 0.f);
+      p.rew[e] = rew;
+      p.success[e] = succ;
+      const int64_t E = p.E;
+      p.extras_f[0 * E + e] = reaching;
+      p.extras_f[1 * E + e] = close;
+      p.extras_f[2 * E + e] = rot;
+      p.extras_f[3 * E + e] = goal;
+      p.extras_f[4 * E + e] = norm(opos - V3{p.obj_default[0], p.obj_default[1], p.obj_default[2]});
+      p.extras_f[5 * E + e] = opos.z;
+      p.extras_f[6 * E + e] = (float)prog;
+      p.extras_b[0 * E + e] = reached;
+      p.extras_b[1 * E + e] = opos.z > 0.1f;
+    }
+  }
+  if (p.do_obs) {
+    __syncthreads();
+    float* dst = p.obs + (int64_t)e0 * obs_dim;
+    for (int i = tid; i < n_env * obs_dim; i += ENV_THREADS) dst[i] = s_obs[i];
+  }
+}
+
 struct FrankaP {
   const float* raw;                              // [E, na_in] policy output in [-1, 1]
   int E, nd, mobile, drive;                      // drive: 0 = 'pos', 1 = 'ik'
@@ -434,6 +578,40 @@ int pm_open_drawer_post_physics(const float* dof_state_all, const float* rigid_b
   const int64_t n_copy = do_obs ? (int64_t)E * ((num_rigid_body + 2) * 13 + (num_dofs + 1) * 2) : 0;
   open_drawer_post_kernel<<<n_env_ctas + pm_cdiv(n_copy, ENV_THREADS * COPY_PER_THREAD), ENV_THREADS, smem, pm_st(s)>>>(p, n_env_ctas);
   PM_CHECK_LAUNCH("pm_open_drawer_post_physics");
+  return PM_OK;
+}
+
+int pm_grasp_cube_obs_dim(int num_dofs) { return 19 + 2 * num_dofs; }
+
+int pm_grasp_cube_post_physics(const float* dof_state, int dofs_per_env, const float* rigid_body, int bodies_per_env, const float* root_tensor,
+                               int n_actors, int obj_actor, int E, int num_dofs, int ltip_rb_index, int rtip_rb_index, const float* dof_lower,
+                               const float* dof_upper, const float* pose_lower_limit, const float* pose_upper_limit, const float* success_pos,
+                               const float* obj_default_pos, float goal_thresh, int do_obs, int do_reward, int advance_progress,
+                               int64_t* progress_buf, float* obs, float* proprio, float* tip_rb, float* tip_rot_9d, float* gripper_length,
+                               float* dof_qpos_normalized, float* rew_buf, uint8_t* success, float* extras_f, uint8_t* extras_b, pm_stream_t s) {
+  PM_REQUIRE(dof_state && rigid_body && root_tensor && pose_lower_limit && pose_upper_limit && success_pos && obj_default_pos, PM_ERR_ARG,
+             "pm_grasp_cube_post_physics: null input");
+  PM_REQUIRE(E > 0 && num_dofs > 2 && num_dofs <= MAX_DOFS && dofs_per_env >= num_dofs && bodies_per_env > 0, PM_ERR_SHAPE,
+             "pm_grasp_cube_post_physics: E=%d num_dofs=%d dofs_per_env=%d bodies_per_env=%d", E, num_dofs, dofs_per_env, bodies_per_env);
+  PM_REQUIRE(ltip_rb_index >= 0 && ltip_rb_index < bodies_per_env && rtip_rb_index >= 0 && rtip_rb_index < bodies_per_env && obj_actor >= 0 &&
+                 obj_actor < n_actors,
+             PM_ERR_SHAPE, "pm_grasp_cube_post_physics: tip / actor index out of range");
+  PM_REQUIRE(do_obs || do_reward, PM_ERR_ARG, "pm_grasp_cube_post_physics: nothing to do");
+  PM_REQUIRE(!do_obs || (dof_lower && dof_upper && obs && tip_rb && tip_rot_9d && gripper_length && dof_qpos_normalized), PM_ERR_ARG,
+             "pm_grasp_cube_post_physics: null observation output");
+  PM_REQUIRE(!do_reward || (rew_buf && success && extras_f && extras_b), PM_ERR_ARG, "pm_grasp_cube_post_physics: null reward output");
+  PM_REQUIRE(!advance_progress || progress_buf, PM_ERR_ARG, "pm_grasp_cube_post_physics: advance_progress without progress_buf");
+  GraspCubeP p;
+  p.dof = dof_state; p.rb = rigid_body; p.root = root_tensor; p.E = E; p.nd = num_dofs; p.nd_all = dofs_per_env; p.nb = bodies_per_env;
+  p.n_actors = n_actors; p.obj_actor = obj_actor; p.ltip = ltip_rb_index; p.rtip = rtip_rb_index; p.dof_lower = dof_lower; p.dof_upper = dof_upper;
+  for (int i = 0; i < 7; ++i) { p.pose_lo[i] = pose_lower_limit[i]; p.pose_hi[i] = pose_upper_limit[i]; }
+  for (int i = 0; i < 3; ++i) { p.success_pos[i] = success_pos[i]; p.obj_default[i] = obj_default_pos[i]; }
+  p.goal_thresh = goal_thresh; p.do_obs = do_obs; p.do_reward = do_reward; p.advance_progress = advance_progress; p.progress = progress_buf;
+  p.obs = obs; p.proprio = proprio; p.tip_rb = tip_rb; p.tip_rot = tip_rot_9d; p.gripper = gripper_length; p.qpos_norm = dof_qpos_normalized;
+  p.rew = rew_buf; p.success = success; p.extras_f = extras_f; p.extras_b = extras_b;
+  const size_t smem = do_obs ? (size_t)ENV_THREADS * (19 + 2 * num_dofs) * sizeof(float) : 0;
+  grasp_cube_post_kernel<<<pm_cdiv(E, ENV_THREADS), ENV_THREADS, smem, pm_st(s)>>>(p);
+  PM_CHECK_LAUNCH("pm_grasp_cube_post_physics");
   return PM_OK;
 }
 

@@ -668,7 +668,7 @@ def _i64(t: Tensor, name: str) -> Tensor:
 class OpenDrawerPostPlan:
     """tasks/open_drawer.py:240-281 + 170-238 (+ load_robot.py:153-164, hand_base.py:388) in ONE launch.  The simulator tensors,
     index tables and result buffers are persistent, so the arguments are validated and converted once; a call costs one ctypes
-    dispatch.  `out` holds the preallocated result tensors (see tasks/open_drawer_step.py:_pm_buffers)."""
+    dispatch.  `out` holds the preallocated result tensors (see tasks/step_kernels.py:_pm_buffers)."""
 
     def __init__(self, dof_state_all: Tensor, rigid_body_all: Tensor, root_tensor: Tensor, obj_actor: int, dof_state_mask: Tensor,
                  rigid_body_mask: Tensor, ltip_rb_index: int, rtip_rb_index: int, dof_lower: Tensor, dof_upper: Tensor, part_bbox_init: Tensor,
@@ -704,6 +704,38 @@ class OpenDrawerPostPlan:
     def __call__(self, do_obs: bool = True, do_reward: bool = True, advance_progress: bool = False) -> None:
         check(lib.pm_open_drawer_post_physics(*self._head, int(do_obs), int(do_reward), int(advance_progress), *self._tail, _stream()),
               "pm_open_drawer_post_physics")
+
+
+class GraspCubePostPlan:
+    """tasks/grasp_cube.py:118-138 + 66-115 (+ load_robot.py:153-164, hand_base.py:388) in ONE launch; arguments converted once."""
+
+    def __init__(self, dof_state: Tensor, rigid_body: Tensor, root_tensor: Tensor, obj_actor: int, num_dofs: int, ltip_rb_index: int,
+                 rtip_rb_index: int, dof_lower: Tensor, dof_upper: Tensor, pose_lower_limit, pose_upper_limit, success_pos, obj_default_pos,
+                 goal_thresh: float, progress_buf: Tensor, out: dict):
+        E = dof_state.shape[0]
+        nd = int(num_dofs)
+        for n, t in (("dof_state", dof_state), ("rigid_body", rigid_body), ("root_tensor", root_tensor), ("dof_lower", dof_lower), ("dof_upper", dof_upper)):
+            assert _f32(t, n).is_contiguous(), n
+        assert dof_state.dim() == 3 and dof_state.shape[2] == 2 and dof_state.shape[1] >= nd
+        assert rigid_body.shape[0] == E and rigid_body.shape[2] == 13 and root_tensor.shape[0] == E and root_tensor.shape[2] == 13
+        assert dof_lower.numel() == nd and dof_upper.numel() == nd and _i64(progress_buf, "progress_buf").numel() == E
+        shapes = dict(obs=(E, 19 + 2 * nd), proprio=(E, 7 + 2 * nd), tip_rb_tensor=(E, 13), tip_rot_9d=(E, 3, 3), gripper_length=(E,),
+                      dof_qpos_normalized=(E, nd), rew_buf=(E,), success=(E,), extras_f=(7, E), extras_b=(2, E))
+        for k, shp in shapes.items():
+            t = out[k]
+            assert t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp, k
+            assert t.dtype == (torch.bool if k in ("success", "extras_b") else torch.float32), k
+        arr = lambda v, n: (ct.c_float * n)(*[float(x) for x in v])
+        self._keep = (dof_state, rigid_body, root_tensor, dof_lower, dof_upper, progress_buf, out)
+        self._head = (_p(dof_state), dof_state.shape[1], _p(rigid_body), rigid_body.shape[1], _p(root_tensor), root_tensor.shape[1], int(obj_actor), E, nd,
+                      int(ltip_rb_index), int(rtip_rb_index), _p(dof_lower), _p(dof_upper), arr(pose_lower_limit, 7), arr(pose_upper_limit, 7),
+                      arr(success_pos, 3), arr(obj_default_pos, 3), float(goal_thresh))
+        self._tail = (_p(progress_buf), _p(out["obs"]), _p(out["proprio"]), _p(out["tip_rb_tensor"]), _p(out["tip_rot_9d"]), _p(out["gripper_length"]),
+                      _p(out["dof_qpos_normalized"]), _p(out["rew_buf"]), _p(out["success"]), _p(out["extras_f"]), _p(out["extras_b"]))
+
+    def __call__(self, do_obs: bool = True, do_reward: bool = True, advance_progress: bool = False) -> None:
+        check(lib.pm_grasp_cube_post_physics(*self._head, int(do_obs), int(do_reward), int(advance_progress), *self._tail, _stream()),
+              "pm_grasp_cube_post_physics")
 
 
 def franka_control(raw_output: Tensor, drive_mode: str, mobile: bool, qpos: Tensor, num_dofs: int, dof_lower: Tensor, dof_upper: Tensor,

@@ -50,7 +50,44 @@ class FrankaKernels:
         return self._pm_root_quat
 
 
-class OpenDrawerKernels:
+class BaseTaskKernels:
+    """tasks/hand_base.py: pre_physics_step (:363-385).  Needs `_pm_flag_buffers()` and `_pm_dof_mask()` from the task mixin."""
+
+    def _pm_flag_buffers(self):
+        fb = getattr(self, "_pm_flags", None)
+        if fb is None:
+            dev, E = self.progress_buf.device, self.num_envs
+            fb = self._pm_flags = dict(reset_buf=torch.zeros(E, device=dev, dtype=torch.bool), reset_succ=torch.zeros(E, device=dev, dtype=torch.bool),
+                                       counts=torch.zeros(4, device=dev, dtype=torch.int32), succ_rate=torch.zeros(1, device=dev))
+        return fb
+
+    def pre_physics_step(self, actions):
+        """hand_base.py:363-385."""
+        out = self._pm_flag_buffers()
+        self.pos_act = self.robot.control(actions)
+        if self.train_test_flag not in ('train', 'test'):
+            raise NotImplementedError
+        train = self.train_test_flag == 'train'
+        if self.success.dtype != torch.bool:
+            self.success = self.success.bool()
+        ops.episode_flags(train, self.rew_buf, self.progress_buf, self.success, self.epis_max_rew, self.epis_max_step, self.explore_step,
+                          self.max_episode_length, out["reset_buf"], out["reset_succ"], out["counts"], out["succ_rate"])
+        self.reset_buf = out["reset_buf"]
+        if train:
+            self.reset_succ = out["reset_succ"]
+            self.extras['succ_rate'] = out["succ_rate"]
+        if int(out["counts"][1]) > 0:                       # the reference's `if self.reset_buf.sum() > 0` (same one host sync)
+            self.reset_idx(self.reset_buf)
+        else:
+            ops.scatter_dof_targets(self.pos_act, self._pm_dof_mask(), self.robot.num_dofs, self.pos_act_all)
+            self._pm_set_targets()
+
+    def _pm_set_targets(self):
+        from isaacgym import gymtorch                      # the simulator binding stays the reference's (hand_base.py:383)
+        self.gym.set_dof_position_target_tensor(self.sim, gymtorch.unwrap_tensor(self.pos_act_all))
+
+
+class OpenDrawerKernels(BaseTaskKernels):
     """tasks/open_drawer.py: compute_observations (:240-281), compute_reward (:170-238); tasks/hand_base.py: pre_physics_step
     (:363-385) and post_physics_step (:387-392)."""
 
@@ -66,9 +103,7 @@ class OpenDrawerKernels:
             return torch.zeros(*shape, device=dev, dtype=torch.float32)
         out = dict(obs=f(E, 29 + 2 * nd), part_bbox=f(E, 8, 3), dof_state_tensor=f(E, nd + 1, 2), rigid_body_tensor=f(E, nb + 2, 13),
                    tip_rb_tensor=f(E, 13), tip_rot_9d=f(E, 3, 3), gripper_length=f(E), dof_qpos_normalized=f(E, nd), rew_buf=f(E),
-                   success=torch.zeros(E, device=dev, dtype=torch.bool), extras_f=f(6, E), extras_b=torch.zeros(3, E, device=dev, dtype=torch.bool),
-                   reset_buf=torch.zeros(E, device=dev, dtype=torch.bool), reset_succ=torch.zeros(E, device=dev, dtype=torch.bool),
-                   counts=torch.zeros(4, device=dev, dtype=torch.int32), succ_rate=f(1))
+                   success=torch.zeros(E, device=dev, dtype=torch.bool), extras_f=f(6, E), extras_b=torch.zeros(3, E, device=dev, dtype=torch.bool))
         self._pm_out = out
         self._pm_const = dict(
             dof_mask=self.dof_state_mask.to(dev, torch.int64).contiguous(), rb_mask=self.rigid_body_mask.to(dev, torch.int64).contiguous(),
@@ -79,6 +114,10 @@ class OpenDrawerKernels:
         self.robot._pm_dof_state_mask = self._pm_const["dof_mask"]
         self.robot._pm_dof_state_all = self.dof_state_tensor_all
         return out
+
+    def _pm_dof_mask(self):
+        self._pm_buffers()
+        return self._pm_const["dof_mask"]
 
     def _pm_launch(self, do_obs, do_reward, advance):
         out = self._pm_buffers()
@@ -125,27 +164,77 @@ class OpenDrawerKernels:
         self._pm_publish_obs(out)
         self._pm_publish_reward(out)
 
-    def pre_physics_step(self, actions):
-        """hand_base.py:363-385."""
-        out = self._pm_buffers()
-        self.pos_act = self.robot.control(actions)
-        if self.train_test_flag not in ('train', 'test'):
-            raise NotImplementedError
-        train = self.train_test_flag == 'train'
-        if self.success.dtype != torch.bool:
-            self.success = self.success.bool()
-        ops.episode_flags(train, self.rew_buf, self.progress_buf, self.success, self.epis_max_rew, self.epis_max_step, self.explore_step,
-                          self.max_episode_length, out["reset_buf"], out["reset_succ"], out["counts"], out["succ_rate"])
-        self.reset_buf = out["reset_buf"]
-        if train:
-            self.reset_succ = out["reset_succ"]
-            self.extras['succ_rate'] = out["succ_rate"]
-        if int(out["counts"][1]) > 0:                       # the reference's `if self.reset_buf.sum() > 0` (same one host sync)
-            self.reset_idx(self.reset_buf)
-        else:
-            ops.scatter_dof_targets(self.pos_act, self._pm_const["dof_mask"], self.robot.num_dofs, self.pos_act_all)
-            self._pm_set_targets()
 
-    def _pm_set_targets(self):
-        from isaacgym import gymtorch                      # the simulator binding stays the reference's (hand_base.py:383)
-        self.gym.set_dof_position_target_tensor(self.sim, gymtorch.unwrap_tensor(self.pos_act_all))
+class GraspCubeKernels(BaseTaskKernels):
+    """tasks/grasp_cube.py: compute_observations (:118-138), compute_reward (:66-115); post_physics_step of tasks/hand_base.py."""
+
+    def _pm_buffers(self):
+        out = getattr(self, "_pm_out", None)
+        if out is not None:
+            return out
+        dev = self.dof_state_tensor.device
+        E, nd = self.num_envs, self.robot.num_dofs
+
+        def f(*shape):
+            return torch.zeros(*shape, device=dev, dtype=torch.float32)
+        out = self._pm_out = dict(obs=f(E, 19 + 2 * nd), proprio=f(E, 7 + 2 * nd), tip_rb_tensor=f(E, 13), tip_rot_9d=f(E, 3, 3), gripper_length=f(E),
+                                  dof_qpos_normalized=f(E, nd), rew_buf=f(E), success=torch.zeros(E, device=dev, dtype=torch.bool), extras_f=f(7, E),
+                                  extras_b=torch.zeros(2, E, device=dev, dtype=torch.bool))
+        self.robot._pm_dof_state_mask = None            # control() reads franka.dof_qpos_raw (a strided view of the simulator tensor)
+        return out
+
+    def _pm_dof_mask(self):
+        return self.dof_state_mask
+
+    def _pm_launch(self, do_obs, do_reward, advance):
+        out = self._pm_buffers()
+        plan = getattr(self, "_pm_plan", None)
+        if plan is None or plan._keep[5] is not self.progress_buf:
+            rob = self.robot
+            plan = self._pm_plan = ops.GraspCubePostPlan(
+                self.dof_state_tensor, self.rigid_body_tensor, self.root_tensor, self.obj_actor, rob.num_dofs, rob.ltip_rb_index, rob.rtip_rb_index,
+                rob.dof_lower_limits_tensor, rob.dof_upper_limits_tensor, self.pose_lower_limit.tolist(), self.pose_upper_limit.tolist(),
+                self.success_pos.reshape(-1).tolist(), self.obj_default_root[:3].tolist(), self.goal_thresh, self.progress_buf, out)
+        plan(do_obs, do_reward, advance)
+        return out
+
+    def _pm_publish_obs(self, out, type="step"):
+        rob, nd = self.robot, self.robot.num_dofs
+        self.obj_root_tensor = self.root_tensor[:, self.obj_actor, :]
+        rob.ltip_rb_tensor = self.rigid_body_tensor[:, rob.ltip_rb_index, :]
+        rob.rtip_rb_tensor = self.rigid_body_tensor[:, rob.rtip_rb_index, :]
+        rob.tip_rb_tensor, rob.tip_pos, rob.tip_rot_9d = out["tip_rb_tensor"], out["tip_rb_tensor"][:, :3], out["tip_rot_9d"]
+        rob.gripper_length, rob.dof_qpos_normalized = out["gripper_length"], out["dof_qpos_normalized"]
+        rob.dof_qpos_raw, rob.dof_qvel_raw = self.dof_state_tensor[:, :nd, 0], self.dof_state_tensor[:, :nd, 1]
+        self.obs_buf['normal_state'] = out["obs"]
+        if self.learn_input_mode == 'mesh_tsdf':        # grasp_cube.py:128-131 (compute_scene_pose is the reference's own; it exits)
+            rot, pos = self.compute_scene_pose()
+            self.obs_buf['mesh_tsdf'] = self.mesh2TSDF.query_tsdf(rot, pos).reshape(self.num_envs, -1)
+        if self.add_proprio_obs and type != 'init':     # grasp_cube.py:133-136: the vision observation gets the proprio columns appended
+            self.obs_buf['proprio_state'] = out["proprio"]
+            vis = self.obs_buf[self.learn_input_mode]
+            D, P = vis.shape[1], out["proprio"].shape[1]
+            cat = getattr(self, "_pm_cat", None)
+            if cat is None or cat.shape != (self.num_envs, D + P):
+                cat = self._pm_cat = torch.empty(self.num_envs, D + P, device=vis.device, dtype=torch.float32)
+            ops.copy_rows(vis, cat[:, :D])
+            ops.copy_rows(out["proprio"], cat[:, D:])
+            self.obs_buf[self.learn_input_mode] = cat
+
+    def _pm_publish_reward(self, out):
+        self.rew_buf, self.success = out["rew_buf"], out["success"]
+        ef, eb, ex = out["extras_f"], out["extras_b"], self.extras
+        ex['reaching_reward'], ex["close_reward"], ex["rot_reward"], ex["reaching_goal_reward"] = ef[0], ef[1], ef[2], ef[3]
+        ex["is_reached"], ex["obj_movement"], ex["raw_reward"], ex["obj_height"], ex["obj_up_flag"], ex["step_id"] = eb[0], ef[4], self.rew_buf, ef[5], eb[1], ef[6]
+
+    def compute_observations(self, type="step"):
+        self._pm_publish_obs(self._pm_launch(True, False, False), type)
+
+    def compute_reward(self, action):
+        self._pm_publish_reward(self._pm_launch(False, True, False))
+
+    def post_physics_step(self, actions):
+        self.refresh_gym_tensor()
+        out = self._pm_launch(True, True, True)
+        self._pm_publish_obs(out)
+        self._pm_publish_reward(out)

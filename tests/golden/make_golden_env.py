@@ -23,10 +23,11 @@ _u.TSDFVolume = _u.gen_camera_pose = _u.TSDFfromMesh = None
 sys.modules["utils"] = _u
 import tasks  # noqa: E402,F401
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from tests.helpers_env import synth_state  # noqa: E402
+from tests.helpers_env import synth_state, synth_state_cube  # noqa: E402
 from tasks.load_robot import franka  # noqa: E402
 
 open_drawer = sys.modules["tasks.open_drawer"].open_drawer
+grasp_cube = sys.modules["tasks.grasp_cube"].grasp_cube
 BaseTask = sys.modules["tasks.hand_base"].BaseTask
 
 
@@ -134,6 +135,51 @@ def run_reference(s, seed):
     return out
 
 
+def run_reference_cube(s, seed, add_proprio=False):
+    """tasks/grasp_cube.py:66-138 on the unmodified class (constructed without its simulator-bound __init__)."""
+    E = s["E"]
+    rob = franka.__new__(franka)
+    rob.device, rob.num_envs, rob.dt, rob.driveMode, rob.mobile = "cpu", E, 1.0 / 60.0, "ik", False
+    rob.num_dofs, rob.ltip_rb_index, rob.rtip_rb_index = s["num_dofs"], s["ltip"], s["rtip"]
+    rob.dof_lower_limits_tensor, rob.dof_upper_limits_tensor = s["dof_lower"].clone(), s["dof_upper"].clone()
+    rob.default_root = torch.tensor([0.0, -0.5, 0.0, 0.0, 0.0, 0.707, 0.707])
+    rob.action_tensor = torch.zeros(E, s["num_dofs"])
+    rob.jacobian_tensor = s["jac"].clone()
+    t = grasp_cube.__new__(grasp_cube)
+    t.num_envs, t.device, t.robot, t.obj_actor = E, "cpu", rob, 1
+    t.reset_range = 0.15
+    t.pose_lower_limit = torch.tensor([-0.15, -0.15, 0.0, -1, -1, -1, -1], dtype=torch.float)
+    t.pose_upper_limit = torch.tensor([0.15, 0.15, 0.4, 1, 1, 1, 1], dtype=torch.float)
+    t.dof_state_tensor, t.rigid_body_tensor, t.root_tensor = s["dof"].clone(), s["rb"].clone(), s["root"].clone()
+    t.goal_thresh = 0.025
+    t.success_pos = torch.tensor([0, 0, 0.2])[None, :]
+    t.obj_default_root = torch.tensor([0, 0, 0.025, 0, 0, 0, 1], dtype=torch.float)
+    t.success = torch.zeros(E).bool()
+    t.obs_buf, t.extras = {}, {}
+    t.progress_buf = torch.zeros(E, dtype=torch.long) + 5
+    t.learn_input_mode, t.add_proprio_obs = ("depth_pc" if add_proprio else "normal_state"), add_proprio
+    out = {}
+    if add_proprio:
+        g = torch.Generator().manual_seed(seed + 9)
+        t.obs_buf["depth_pc"] = torch.randn(E, 48, generator=g)
+        out["vision_obs"] = t.obs_buf["depth_pc"].clone()
+    t.compute_observations()
+    out["obs"] = t.obs_buf["normal_state"].clone()
+    if add_proprio:
+        out["proprio_state"], out["vision_cat"] = t.obs_buf["proprio_state"].clone(), t.obs_buf["depth_pc"].clone()
+    for k in ("tip_rb_tensor", "tip_rot_9d", "gripper_length", "dof_qpos_normalized", "dof_qpos_raw", "dof_qvel_raw"):
+        out["robot_" + k] = getattr(t.robot, k).clone()
+    t.compute_reward(None)
+    out["rew_buf"], out["success"] = t.rew_buf.clone(), t.success.clone()
+    for k, v in t.extras.items():
+        out["extras_" + k] = v.clone().float() if v.dtype == torch.bool else v.clone()
+    g = torch.Generator().manual_seed(seed + 2)
+    a = torch.rand(E, 7, generator=g) * 2 - 1
+    out["actions"] = a
+    out["action_tensor_ik_fixed"] = t.robot.control(a).clone()
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     s = synth_state(96, 20260)
@@ -146,3 +192,13 @@ if __name__ == "__main__":
     for k in ("extras_is_reached", "extras_is_grasped", "success", "extras_is_open", "train_reset_buf", "test_reset_buf"):
         print(k, float(out[k].float().mean()))
     print("rew", out["rew_buf"][:6], "succ_rate", out["train_succ_rate"], "reset calls", out["train_reset_called"])
+    sc = synth_state_cube(96, 20261)
+    rec = {"in_" + k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in sc.items()}
+    oc = run_reference_cube(sc, 20261)
+    rec.update({k: v.numpy() for k, v in oc.items()})
+    rec.update({"pp_" + k: v.numpy() for k, v in run_reference_cube(sc, 20261, add_proprio=True).items() if k in ("vision_obs", "proprio_state", "vision_cat")})
+    path = os.path.join(HERE, "env_grasp_cube.npz")
+    np.savez_compressed(path, **rec)
+    print("wrote", path, os.path.getsize(path), "bytes")
+    for k in ("extras_is_reached", "success", "extras_obj_up_flag"):
+        print(k, float(oc[k].float().mean()))

@@ -91,3 +91,31 @@ def synth_state(E, seed, num_dofs=12, nb_robot=14, ltip=12, rtip=13, num_objs=5)
                 dof_mask=dof_mask, rb_mask=rb_mask, dof_all=dof_all, rb_all=rb_all, root=root, part_bbox_init=part_bbox_init,
                 part_axis_dir_init=part_axis_dir_init, part_joint_upper_limits=part_joint_upper_limits,
                 part_joint_lower_limits=part_joint_lower_limits, dof_lower=dof_lower, dof_upper=dof_upper, jac=jac)
+
+
+def synth_state_cube(E, seed, num_dofs=9, nb=13, ltip=10, rtip=11):
+    """grasp_cube simulator state (regular per-env tensors, tasks/grasp_cube.py:25-33): a mix of grippers on / off the cube and
+    cubes at / away from the goal; one env sits at the identity rotation (a 24-way tie of deambiguity_rotation is impossible,
+    but several candidates coincide in angle there)."""
+    g = torch.Generator().manual_seed(seed)
+    dof = torch.randn(E, num_dofs, 2, generator=g)
+    rb = torch.randn(E, nb, 13, generator=g)
+    root = torch.randn(E, 2, 13, generator=g)
+    dof_lower = -2.5 + 0.5 * torch.rand(num_dofs, generator=g)
+    dof_upper = 2.5 + 0.5 * torch.rand(num_dofs, generator=g)
+    at_goal = torch.rand(E, generator=g) < 0.35
+    pos = torch.where(at_goal[:, None], torch.tensor([0.0, 0.0, 0.2]) + 0.015 * torch.randn(E, 3, generator=g),
+                      torch.tensor([0.0, 0.0, 0.06]) + torch.tensor([0.15, 0.15, 0.08]) * (torch.rand(E, 3, generator=g) * 2 - 1))
+    root[:, 1, :3] = pos
+    root[:, 1, 3:7] = rand_quat(g, E, 1.0)
+    root[0, 1, 3:7] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+    near = torch.rand(E, generator=g) < 0.6
+    off = torch.where(near[:, None], 0.008 * torch.randn(E, 3, generator=g), 0.2 * torch.randn(E, 3, generator=g))
+    half = torch.tensor([0.0, 1.0, 0.0]) * (0.02 + 0.03 * torch.rand(E, 1, generator=g))
+    rb[:, ltip, :3] = pos + off + half
+    rb[:, rtip, :3] = pos + off - half
+    q = rand_quat(g, E, 0.5)
+    rb[:, ltip, 3:7] = q + 0.01 * torch.randn(E, 4, generator=g)
+    rb[:, rtip, 3:7] = q + 0.01 * torch.randn(E, 4, generator=g)
+    jac = torch.randn(E, nb - 2, 6, num_dofs, generator=g)
+    return dict(E=E, num_dofs=num_dofs, nb=nb, ltip=ltip, rtip=rtip, dof=dof, rb=rb, root=root, dof_lower=dof_lower, dof_upper=dof_upper, jac=jac)

@@ -206,3 +206,111 @@ def test_full_size_vs_oracle(E, seed):
     assert bool((t.progress_buf == 4).all()) and close(t.extras["step_id"], torch.full((E,), 4.0))[0]
     if E >= 129:
         assert 0.02 < float(r["success"].float().mean()) < 0.6
+
+
+# ---------------------------------------------------------------------------------------------------------------- grasp_cube
+def make_cube_task(s, add_proprio=False, vision=None):
+    from partmanip_b200.tasks import FrankaKernels, GraspCubeKernels
+    from tests.helpers_env import synth_state_cube  # noqa: F401
+
+    class Robot(FrankaKernels):
+        pass
+
+    class Task(GraspCubeKernels):
+        def refresh_gym_tensor(self):
+            pass
+
+        def reset_idx(self, buf):
+            self.reset_calls.append(buf.clone())
+
+        def _pm_set_targets(self):
+            self.targets_set += 1
+
+    E, nd = int(s["E"]), int(s["num_dofs"])
+    rob = Robot()
+    rob.device, rob.num_envs, rob.dt, rob.driveMode, rob.mobile = DEV, E, 1.0 / 60.0, "ik", False
+    rob.num_dofs, rob.ltip_rb_index, rob.rtip_rb_index = nd, int(s["ltip"]), int(s["rtip"])
+    rob.dof_lower_limits_tensor, rob.dof_upper_limits_tensor = s["dof_lower"].to(DEV), s["dof_upper"].to(DEV)
+    rob.default_root = torch.tensor([0.0, -0.5, 0.0, 0.0, 0.0, 0.707, 0.707], device=DEV)
+    rob.jacobian_tensor = s["jac"].to(DEV)
+    t = Task()
+    t.num_envs, t.device, t.robot, t.obj_actor = E, DEV, rob, 1
+    t.pose_lower_limit = torch.tensor([-0.15, -0.15, 0.0, -1, -1, -1, -1], device=DEV, dtype=torch.float)
+    t.pose_upper_limit = torch.tensor([0.15, 0.15, 0.4, 1, 1, 1, 1], device=DEV, dtype=torch.float)
+    t.dof_state_tensor, t.rigid_body_tensor, t.root_tensor = s["dof"].to(DEV), s["rb"].to(DEV), s["root"].to(DEV)
+    t.goal_thresh = 0.025
+    t.success_pos = torch.tensor([0, 0, 0.2], device=DEV)[None, :]
+    t.obj_default_root = torch.tensor([0, 0, 0.025, 0, 0, 0, 1], device=DEV, dtype=torch.float)
+    t.success = torch.zeros(E, device=DEV).bool()
+    t.obs_buf, t.extras = {}, {}
+    t.progress_buf = torch.zeros(E, dtype=torch.long, device=DEV) + 5
+    t.rew_buf = torch.zeros(E, device=DEV)
+    t.epis_max_rew = -100 * torch.ones(E, device=DEV)
+    t.epis_max_step = torch.zeros(E, dtype=torch.long, device=DEV)
+    t.explore_step, t.max_episode_length, t.train_test_flag = 40, 200, "train"
+    t.pos_act_all = torch.zeros(E * nd, device=DEV)
+    t.dof_state_mask = torch.arange(E * nd, device=DEV).reshape(E, -1)
+    t.learn_input_mode, t.add_proprio_obs = ("depth_pc" if add_proprio else "normal_state"), add_proprio
+    if vision is not None:
+        t.obs_buf["depth_pc"] = vision.to(DEV)
+    t.reset_calls, t.targets_set = [], 0
+    return t
+
+
+def test_grasp_cube_vs_reference_recordings():
+    g = load_golden("env_grasp_cube.npz")
+    s = {k[3:]: v for k, v in g.items() if k.startswith("in_")}
+    t = make_cube_task(s)
+    t.compute_observations()
+    assert t.obs_buf["normal_state"].shape == (96, 37)
+    for got, key in ((t.obs_buf["normal_state"], "obs"), (t.robot.tip_rb_tensor, "robot_tip_rb_tensor"), (t.robot.tip_rot_9d, "robot_tip_rot_9d"),
+                     (t.robot.gripper_length, "robot_gripper_length"), (t.robot.dof_qpos_normalized, "robot_dof_qpos_normalized"),
+                     (t.robot.dof_qpos_raw, "robot_dof_qpos_raw"), (t.robot.dof_qvel_raw, "robot_dof_qvel_raw")):
+        ok, err = close(got, g[key])
+        assert ok, (key, err)
+    t.compute_reward(None)
+    ok, err = close(t.rew_buf, g["rew_buf"])
+    assert ok, ("rew_buf", err)
+    assert torch.equal(t.success.cpu(), g["success"].bool())
+    for k in ("is_reached", "obj_up_flag"):
+        assert t.extras[k].dtype == torch.bool and torch.equal(t.extras[k].cpu().float(), g["extras_" + k].float()), k
+    for k in ("reaching_reward", "close_reward", "rot_reward", "reaching_goal_reward", "obj_movement", "raw_reward", "obj_height", "step_id"):
+        ok, err = close(t.extras[k], g["extras_" + k])
+        assert ok, (k, err)
+    a = t.robot.control(g["actions"].to(DEV))
+    assert float((a.cpu() - g["action_tensor_ik_fixed"]).abs().max()) <= 2e-4
+    # vision mode with proprioception appended to the observation (grasp_cube.py:133-136); type='init' leaves it alone
+    t2 = make_cube_task(s, add_proprio=True, vision=g["pp_vision_obs"])
+    t2.compute_observations(type="init")
+    assert "proprio_state" not in t2.obs_buf and t2.obs_buf["depth_pc"].shape == (96, 48)
+    t2.compute_observations()
+    assert close(t2.obs_buf["proprio_state"], g["pp_proprio_state"])[0] and close(t2.obs_buf["depth_pc"], g["pp_vision_cat"])[0]
+    assert torch.equal(t2.obs_buf["depth_pc"][:, :48].cpu(), g["pp_vision_obs"])
+
+
+def test_grasp_cube_step_cycle_full_size():
+    """2048 envs (the shipped ppo.yaml env count): one post-physics launch, then the generic pre-physics step; vs the pinned oracle."""
+    from partmanip_b200 import ops
+    from tests.helpers_env import synth_state_cube
+    E = 2048
+    s = synth_state_cube(E, 17)
+    t = make_cube_task(s)
+    t._pm_buffers()
+    n0 = ops.launch_count()
+    t.post_physics_step(None)
+    assert ops.launch_count() - n0 == 1 and bool((t.progress_buf == 6).all())
+    lo, hi = t.pose_lower_limit.cpu(), t.pose_upper_limit.cpu()
+    o = EO.cube_observations(s["dof"], s["rb"], s["root"], 1, s["num_dofs"], s["ltip"], s["rtip"], s["dof_lower"], s["dof_upper"], lo, hi)
+    r = EO.cube_reward(o["robot"], o["obj_root"], torch.tensor([0, 0, 0.2])[None, :], 0.025, torch.tensor([0.0, 0.0, 0.025]))
+    # deambiguity_rotation picks among 24 candidates by angle: a near-tie may resolve differently (then 9 obs entries differ)
+    row_bad = ((t.obs_buf["normal_state"].cpu() - o["obs"]).abs() > 1e-5 * (1 + o["obs"].abs())).any(dim=1)
+    flips = (t.extras["is_reached"].cpu() != r["is_reached"]) | (t.success.cpu() != r["success"].bool()) | row_bad
+    assert int(flips.sum()) <= 2, int(flips.sum())
+    keep = ~flips
+    ok, err = close(t.rew_buf[keep.to(DEV)], r["rew_buf"][keep])
+    assert ok, err
+    acts = torch.rand(E, 7, device=DEV) * 2 - 1
+    t.pre_physics_step(acts)
+    f = EO.episode_flags("train", t.rew_buf.cpu(), t.progress_buf.cpu(), t.success.cpu(), -100 * torch.ones(E), torch.zeros(E, dtype=torch.long), 40, 200)
+    assert torch.equal(t.reset_buf.cpu(), f["reset_buf"]) and torch.equal(t.epis_max_step.cpu(), f["epis_max_step"])
+    assert torch.equal(t.extras["succ_rate"].cpu(), f["succ_rate"]) and len(t.reset_calls) == int(bool(f["reset_buf"].any()))

@@ -63,3 +63,22 @@ def test_episode_flags_bit_exact():
     assert torch.equal(f["succ_rate"], g["train_succ_rate"])
     f = EO.episode_flags("test", g["rew_buf"], g["pre_progress_buf"], g["success"].bool(), f["epis_max_rew"], f["epis_max_step"], 40, 60)
     assert torch.equal(f["reset_buf"], g["test_reset_buf"])
+
+
+def test_grasp_cube_bit_exact():
+    """tasks/grasp_cube.py:66-138 (incl. deambiguity_rotation, utils/torch_jit_utils.py:412-425) against the recordings."""
+    g = load_golden("env_grasp_cube.npz")
+    lo = torch.tensor([-0.15, -0.15, 0.0, -1, -1, -1, -1], dtype=torch.float)
+    hi = torch.tensor([0.15, 0.15, 0.4, 1, 1, 1, 1], dtype=torch.float)
+    o = EO.cube_observations(g["in_dof"], g["in_rb"], g["in_root"], 1, int(g["in_num_dofs"]), int(g["in_ltip"]), int(g["in_rtip"]), g["in_dof_lower"],
+                             g["in_dof_upper"], lo, hi)
+    assert torch.equal(o["obs"], g["obs"]) and o["obs"].shape[1] == 37 and torch.equal(o["proprio"], g["pp_proprio_state"])
+    assert torch.equal(torch.cat((g["pp_vision_obs"], o["proprio"]), dim=-1), g["pp_vision_cat"])
+    r = EO.cube_reward(o["robot"], o["obj_root"], torch.tensor([0, 0, 0.2])[None, :], 0.025, torch.tensor([0.0, 0.0, 0.025]))
+    assert torch.equal(r["rew_buf"], g["rew_buf"]) and torch.equal(r["success"].bool(), g["success"].bool())
+    for k in ("reaching_reward", "close_reward", "rot_reward", "is_reached", "reaching_goal_reward", "obj_movement", "raw_reward", "obj_height", "obj_up_flag"):
+        assert torch.equal(r[k].float(), g["extras_" + k].float()), k
+    assert 0.05 < float(r["success"].float().mean()) < 0.6 and 0.2 < float(r["is_reached"].float().mean()) < 0.9
+    a = EO.control(g["actions"], "ik", False, o["robot"]["dof_qpos_raw"], 1 / 60, None, g["in_dof_lower"], g["in_dof_upper"], g["in_jac"],
+                   int(g["in_ltip"]), int(g["in_rtip"]))
+    assert torch.equal(a, g["action_tensor_ik_fixed"])
