@@ -50,6 +50,7 @@ class RolloutStorage:
             for name, width in (("tea_obs", tea_obs_shape), ("observations", obs_shape), ("succ_flag", 1)):
                 setattr(self, name, torch.zeros(rows, width, device=device))
             self.mix_buf_ind = self.cur_buf_size = self.last_episode_buf_ind = 0
+            self.rows_added = 0         # total rows ever written (lets a label cache notice rows it has not seen)
             self.succ_buf_ind = (max_length or 0) * num_envs
         else:                           # PPO (storage.py:28-41): (T, E, .) arrays, always full
             widths = {"obs": obs_shape, "act": actions_shape, 1: 1}
@@ -83,6 +84,7 @@ class RolloutStorage:
         i = self.mix_buf_ind
         ops.copy_rows(stu_obs, self.observations[i:i + self.num_envs])
         ops.copy_rows(tea_obs, self.tea_obs[i:i + self.num_envs])
+        self.rows_added += self.num_envs
         max_buf_size = self.n_steps * self.num_envs
         self.mix_buf_ind = (self.mix_buf_ind + self.num_envs) % max_buf_size
         if self.cur_buf_size < max_buf_size:

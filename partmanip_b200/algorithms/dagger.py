@@ -62,6 +62,13 @@ class dagger:
         self._stats = torch.zeros(2, device=self.device)
         self._acc = torch.zeros(2, device=self.device)
         self._mb = {}
+        # The teacher is frozen and `act` is deterministic row by row, so its label for a ring row never changes: compute it once
+        # when the row enters the ring instead of once per minibatch visit (n_updates * n_minibatches teacher forwards per
+        # iteration in dagger.py:311).  Bit-identical to recomputing (tests/test_gpu_dagger.py); cfg['cache_teacher_actions'] = False
+        # restores the per-minibatch teacher forward.
+        self.cache_teacher_actions = bool(cfg.get('cache_teacher_actions', True))
+        self._tea_act = torch.zeros(self.buf_size * self.num_envs, self.num_actions, device=self.device) if self.cache_teacher_actions else None
+        self._rows_labelled = 0
 
     def _build_student(self, proprio_dim):
         """dagger.py:53-56: one Adam over all student parameters, in `student.parameters()` order [log_std, actor.*, critic.*].
@@ -156,7 +163,11 @@ class dagger:
         for _ in range(self.n_steps):
             actions = self.student.random_act(stu_obs)
             nxt, rews, _, infos = self.vec_env.step(actions)
+            slot = self.storage.mix_buf_ind
             self.storage.add_transitions_dagger(stu_obs, tea_obs)
+            if self.cache_teacher_actions:
+                ops.copy_rows(self.teacher.act(tea_obs), self._tea_act[slot:slot + self.num_envs])
+                self._rows_labelled += self.num_envs
             episode.append(deepcopy(_action_summaries(infos, actions)))
             stu_obs, tea_obs = nxt[self.stu_obs_mode], nxt[self.tea_obs_mode]
             if self.reward_reset:                                   # dagger.py:228-233: restart envs that fall behind the teacher
@@ -234,14 +245,21 @@ class dagger:
         self._acc.zero_()
         count = 0
         dmu = None
+        if self.cache_teacher_actions and self._rows_labelled != st.rows_added:
+            # rows entered the ring behind the cache's back (storage used directly): label the whole live buffer once
+            n = st.cur_buf_size
+            ops.copy_rows(self.teacher.act(st.tea_obs[:n]), self._tea_act[:n])
+            self._rows_labelled = st.rows_added
         for epoch in range(self.n_updates):
             for indices in st.mini_batch_generator(self.num_mini_batches):
                 stu_obs = self._gather(st.observations, indices, 's')
-                tea_obs = self._gather(st.tea_obs, indices, 't')
                 B = stu_obs.shape[0]
                 if dmu is None or dmu.shape[0] != B:
                     dmu = torch.empty(B, self.num_actions, device=self.device)
-                tea_act = self.teacher.act(tea_obs)
+                if self.cache_teacher_actions:
+                    tea_act = self._gather(self._tea_act, indices, 'a')
+                else:
+                    tea_act = self.teacher.act(self._gather(st.tea_obs, indices, 't'))
                 mu = stu.actor.runner.forward(stu_obs)
                 ops.dagger_loss(mu, tea_act, stu.max_action, squash, 1.0 / (B * self.num_actions), self._stats, dmu)
                 ops.accumulate(self._stats, 1.0, self._acc, 0)

@@ -92,3 +92,34 @@ def test_dagger_ring_buffer_wraps_and_small_buffer_skips_update(tmp_path):
     batches = list(st.mini_batch_generator(2))
     assert len(batches) == 2 and all(b.numel() == 4 for b in batches)
     assert sorted(torch.cat(batches).tolist()) == list(range(8))
+
+
+def test_cached_teacher_labels_are_bit_identical_to_recomputing(tmp_path):
+    """The frozen teacher's label of a ring row never changes: labelling rows once at insertion (default) and running the teacher on
+    every minibatch visit (dagger.py:311, cfg cache_teacher_actions=False) give bit-identical students — random sampler, wrapped ring."""
+    from partmanip_b200.algorithms import dagger
+    from partmanip_b200.envs import FakeVecEnv
+    E, A, Dt, D = 16, 10, 53, 1024 * 3
+    g = torch.Generator().manual_seed(4)
+    tea_cfg = dict(action_std=0.5, action_activate="tanh", clipAction=1.0, network=dict(name="MLP", hid_dim=[512, 512, 512], activation="tanh"))
+    tea_sd = {f"actor.{k}": v for k, v in O.mlp_init(Dt, A, [512, 512, 512], gen=g).items()}
+    tea_sd.update({f"critic.{k}": v for k, v in O.mlp_init(Dt, 1, [512, 512, 512], gen=g).items()})
+    tea_sd["log_std"] = torch.full((A,), -0.69)
+    path = str(tmp_path / "teacher.pth")
+    torch.save(dict(obs_mode="state", model_cfg=tea_cfg, model_state_dict=tea_sd, tricks=dict(use_state_norm=False)), path)
+    net = dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, point_num=1024, precision="bf16")
+    runs = []
+    for cache in (True, False):
+        torch.manual_seed(9)
+        env = FakeVecEnv(E, D, A, DEV, cloud=True, seed=5, extra_obs={"state": Dt})
+        r = dagger(env, _cfg(E, net, path, buf_size=12, n_steps=8, max_iterations=3, sampler="random", cache_teacher_actions=cache), _Logger())
+        if runs:
+            r.student.load_state_dict(runs[0][0])
+        init = {k: v.detach().clone() for k, v in r.student.state_dict().items()}
+        torch.manual_seed(10)
+        r.run()                                                  # 3 iterations x 8 steps into a 12-step ring: wraps twice
+        runs.append((init, {k: v.detach().clone() for k, v in r.student.state_dict().items()}, r.log_dict["Train/dagger_loss"]))
+    assert runs[0][2] == runs[1][2]
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    assert any(not torch.equal(runs[0][1][k], runs[0][0][k]) for k in runs[0][1] if k.startswith("actor."))
