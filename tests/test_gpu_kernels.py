@@ -309,6 +309,23 @@ def test_gather_and_copy_rows(ops):
     assert torch.equal(big[:, 10:47], narrow) and float(big[:, :10].abs().sum()) == 0.0
 
 
+def test_gather_rows_beyond_2_31_elements(ops):
+    """Maximum sizes: a DAgger ring past 2^31 floats (360 k rows of a 2048-point cloud = 8.8 GB; the shipped buf_size 1600 x 2048 envs
+    would be 80 GB and fits a B200) — row offsets are 64-bit, rows at the far end gather and append correctly."""
+    rows, D = 360_000, 6144
+    assert rows * D > 2 ** 31
+    ring = torch.empty(rows, D, device=DEV)
+    far = torch.tensor([rows - 1, rows - 7, 350_001, 349_525, 5], device=DEV)          # 349_525 * 6144 is just below 2^31, 350_001 above
+    marks = torch.arange(5, device=DEV, dtype=torch.float32)[:, None] + torch.linspace(0, 1, D, device=DEV)[None, :]
+    ops.copy_rows(marks[:2], ring[rows - 2:rows])                                       # append at the very end (storage.py:84-91)
+    assert torch.equal(ring[rows - 2:], marks[:2])
+    ring[far] = marks
+    out = ops.gather_rows(ring, far, torch.empty(5, D, device=DEV))
+    assert torch.equal(out, marks)
+    del ring
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------------ KAT-1
 def test_kat1_shipped_checkpoint_through_actor_critic(ops):
     from partmanip_b200.algorithms.algo_utils import ActorCritic
