@@ -11,6 +11,12 @@
 //            deterministic, no atomics), fused with the previous activation's derivative.
 //   flatten  (B, 27, 32) channels-last <-> (B, 32*27 [+ proprio]) channel-major rows, the order x.reshape(batch, -1) gives the
 //            reference's final_mlp (network.py:92-96).
+// Measured alternatives for the first layer (round 2, not kept; per 2048 volumes, conv1_fwd_kernel = 2.3 ms, conv1_dw_kernel = 2.7 ms):
+//  * an implicit-im2col GEMM on the tcgen05 dense kernel (A tiles gathered straight from the volume, three-term split, MMA 16 columns
+//    wide): correct, 5.9 ms forward / 4.4 ms weight gradient — with one input channel every gathered element feeds only 16
+//    multiply-adds, which does not pay for its index arithmetic, split into bf16 terms and shared-memory image store;
+//  * the weights in constant memory (FFMA with uniform-register operands, one shared load per tap): correct, 3.3 ms — the uniform
+//    datapath has to deliver a fresh operand for every FFMA and becomes the limiter.
 #include "common.cuh"
 
 namespace {

@@ -75,14 +75,17 @@ __device__ __forceinline__ void load_tile(TileRegs& r, const float* __restrict__
 __device__ __forceinline__ float bf16_hi_as_f32(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ float bf16_lo_as_f32(uint32_t w) { return __uint_as_float(w << 16); }
 
+// mn_used: the MMA reads only the first mn_used (multiple of 16) MN indices of the tile: chunks beyond are not stored
 template <bool MN_MAJOR, int PARTS>
-__device__ __forceinline__ void store_tile(const TileRegs& r, uint8_t* base /* PARTS images, IMG_BYTES apart */, int tid) {
+__device__ __forceinline__ void store_tile(const TileRegs& r, uint8_t* base /* PARTS images, IMG_BYTES apart */, int tid, int mn_used = 128) {
 #pragma unroll
   for (int j = 0; j < CHUNKS_PER_THREAD; ++j) {
     const int i = tid + j * GT_THREADS;
     uint32_t off;
-    if (MN_MAJOR) { const uint32_t kr = i >> 4, c16 = i & 15; off = (c16 >> 3) * 8192u + kr * 128u + (((c16 & 7u) ^ (kr & 7u)) << 4); }
-    else          { const uint32_t row = i >> 3, c = i & 7;   off = row * 128u + ((c ^ (row & 7u)) << 4); }
+    if (MN_MAJOR) { const uint32_t kr = i >> 4, c16 = i & 15; off = (c16 >> 3) * 8192u + kr * 128u + (((c16 & 7u) ^ (kr & 7u)) << 4);
+                    if ((int)(c16 * 8) >= mn_used) continue; }
+    else          { const uint32_t row = i >> 3, c = i & 7;   off = row * 128u + ((c ^ (row & 7u)) << 4);
+                    if ((int)row >= mn_used) continue; }
     float res[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) res[e] = r.v[j][e];
@@ -165,7 +168,9 @@ gemm_tc_kernel(const GemmTcP p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = umma_idesc_ex(TBM, TBN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  // the MMA is as wide as this CTA's live columns, in steps of 16 (a 16-wide output layer costs an eighth of the tensor time of N = 128)
+  const int n_used = min(TBN, (p.N - n0 + 15) / 16 * 16);
+  const uint32_t idesc = umma_idesc_ex(TBM, n_used, A_MN ? 1 : 0, B_MN ? 1 : 0);
   bool ok = true;
 
   TileRegs ra, rb;
@@ -188,7 +193,7 @@ gemm_tc_kernel(const GemmTcP p) {
     }
     uint8_t* st = smem + s * Plan::STAGE;
     store_tile<A_MN, PARTS>(ra, st, tid);
-    store_tile<B_MN, PARTS>(rb, st + PARTS * IMG_BYTES, tid);
+    store_tile<B_MN, PARTS>(rb, st + PARTS * IMG_BYTES, tid, n_used);
     if (kb + 1 < nkb) {                          // next block's global loads fly during the barrier and the MMA issue
       load_tile<A_MN>(ra, p.A, p.lda, m0, k_begin + (kb + 1) * TBK, M, k_end, tid);
       load_tile<B_MN>(rb, p.B, p.ldb, n0, k_begin + (kb + 1) * TBK, p.N, k_end, tid);
@@ -233,6 +238,7 @@ gemm_tc_kernel(const GemmTcP p) {
     if (EPI == EPI_DW) C += (int64_t)blockIdx.z * p.M * p.ldc;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {             // 16 columns at a time: the next tile's prefetched operands (64 registers) stay live
+      if (half * 64 + cc * 16 >= n_used) break;  // warp-uniform: columns the MMA never produced
       uint32_t v[16];
       if (nkb > 0) {
         tmem_ld16(taddr + cc * 16, v);
