@@ -356,13 +356,19 @@ int pm_conv3d_im2col(const float* in, int64_t ld_in, int64_t sample_stride, int 
 /* adjoint of im2col in gather form (deterministic), times act'(y): din[(b, voxel), c] = (sum of covering patch entries) * act'(y[...]) */
 int pm_conv3d_col2im(const float* dcols, int Kpad, int B, int C, int Din, int k, int s, const float* y, int act, float* din,
                      pm_stream_t st);
-/* The first layer, Conv3d(1, 16, k 5, stride 3, padding 2) + activation (network.py:70, 122), directly on the volume rows
+/* The first layer, Conv3d(1, 16, k 5, stride `stride`, padding 2) + activation (network.py:70, 104, 122), directly on the volume rows
  * x (B, >= Din^3) in exact fp32 — no patch matrix (it would be 5 GB at 2048 samples): y ((b, voxel'), 16) channels-last.
  * pm_conv3d_first_backward: dW (16,1,5,5,5) from dpre ((b, voxel'), 16); its bias gradient is a column sum of dpre. */
-int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, const float* w, const float* bias, int act, float* y,
+int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, int stride, const float* w, const float* bias, int act, float* y,
                             pm_stream_t st);
 size_t pm_conv3d_first_backward_ws_bytes(void);
-int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, const float* dpre, float* dW, void* ws, pm_stream_t st);
+int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, int stride, const float* dpre, float* dW, void* ws, pm_stream_t st);
+/* nn.MaxPool3d(kernel_size = k) (stride k, no padding) of PoolConv3DNet (network.py:100-117) on channels-last rows y ((b, voxel), C):
+ * out ((b, cell), C), argmax ((b, cell), C) = index of the winning voxel inside the sample (first maximum in (d, h, w) scan order).
+ * backward: dpre ((b, voxel), C) = dout routed to the winning voxel, times act'(y) (y = the activation output that was pooled). */
+int pm_maxpool3d_forward(const float* y, int B, int C, int Din, int k, float* out, int32_t* argmax, pm_stream_t st);
+int pm_maxpool3d_backward(const float* dout, const int32_t* argmax, const float* y, int act, int B, int C, int Din, int k, float* dpre,
+                          pm_stream_t st);
 /* to_rows != 0: out[b*ld_row + c*P + pos] = in[(b*P + pos)*C + c] (channels-last -> x.reshape(batch, -1) order, network.py:92-96);
  * to_rows == 0: out[(b*P + pos)*C + c] = in[b*ld_row + c*P + pos] */
 int pm_conv3d_flatten(const float* in, float* out, int B, int P, int C, int64_t ld_row, int to_rows, pm_stream_t st);

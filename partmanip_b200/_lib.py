@@ -84,9 +84,11 @@ SIGNATURES = {
     "pm_conv3d_im2col": (I, [P, L, L, I, I, I, I, I, P, I, P]),
     "pm_conv3d_col2im": (I, [P, I, I, I, I, I, I, P, I, P, P]),
     "pm_conv3d_flatten": (I, [P, P, I, I, I, L, I, P]),
-    "pm_conv3d_first_forward": (I, [P, L, I, I, P, P, I, P, P]),
+    "pm_conv3d_first_forward": (I, [P, L, I, I, I, P, P, I, P, P]),
     "pm_conv3d_first_backward_ws_bytes": (SZ, []),
-    "pm_conv3d_first_backward": (I, [P, L, I, I, P, P, P, P]),
+    "pm_conv3d_first_backward": (I, [P, L, I, I, I, P, P, P, P]),
+    "pm_maxpool3d_forward": (I, [P, I, I, I, I, P, P, P]),
+    "pm_maxpool3d_backward": (I, [P, P, P, I, I, I, I, I, P, P]),
     "pm_mesh2sdf_query": (I, [P, L, P, P, P, I, I, I, P, P, P, I, I, C.POINTER(F), F, P, P]),
     "pm_open_drawer_obs_dim": (I, [I]),
     "pm_open_drawer_post_physics": (I, [P, P, P, I, I, P, P, I, I, I, I, I, P, P, P, P, P, P, P, F, I, I, I, P,

@@ -14,9 +14,9 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from .network import MLP, Conv3DNet, PointNet  # noqa: F401  (resolved by name, like the reference's eval())
+from .network import MLP, Conv3DNet, PointNet, PoolConv3DNet  # noqa: F401  (resolved by name, like the reference's eval())
 
-_NETWORKS = {"MLP": MLP, "PointNet": PointNet, "Conv3DNet": Conv3DNet}
+_NETWORKS = {"MLP": MLP, "PointNet": PointNet, "Conv3DNet": Conv3DNet, "PoolConv3DNet": PoolConv3DNet}
 
 
 class ActorCritic(nn.Module):
@@ -25,9 +25,9 @@ class ActorCritic(nn.Module):
         super().__init__()
         net_cfg = model_cfg['network']
         if net_cfg['name'] not in _NETWORKS:
-            # the reference eval()s the name (actor_critic.py:16); PoolConv3DNet/ResNet/depthResNet are image / pooled students
-            # outside the hot path and its next rows
-            raise NotImplementedError(f"network {net_cfg['name']!r} is outside the B200 hot path (MLP, PointNet, Conv3DNet)")
+            # the reference eval()s the name (actor_critic.py:16); ResNet / depthResNet are image students outside the hot path and its
+            # next rows
+            raise NotImplementedError(f"network {net_cfg['name']!r} is outside the B200 hot path (MLP, PointNet, Conv3DNet, PoolConv3DNet)")
         cls = _NETWORKS[net_cfg['name']]
         self.actor = cls(obs_shape, actions_shape, net_cfg, proprio_shape=proprio_shape)     # policy
         self.critic = cls(obs_shape, 1, net_cfg, proprio_shape=proprio_shape)                # value function

@@ -244,6 +244,8 @@ class _Conv3DRunner(_Runner):
     """Conv3DNet on the kernels: per convolution pm_conv3d_im2col + a dense layer on tcgen05 (channels-last activations), the head as
     two dense layers; backward = the dense backward + pm_conv3d_col2im."""
     SPECS = ((1, 16, 5, 3), (16, 32, 3, 3), (32, 32, 3, 2))          # (Cin, Cout, k, stride): network.py:70
+    POOL = 0                                                         # PoolConv3DNet: nn.MaxPool3d(POOL) after the encoder
+    HID = 256                                                        # width of final_mlp's hidden layer
 
     def _get(self, B: int, dev):
         b = self._bufs.get(B)
@@ -259,9 +261,13 @@ class _Conv3DRunner(_Runner):
                 b["y"].append(torch.empty(rows, co, device=dev))
                 b["dcols"].append(torch.empty(rows, kpad, device=dev) if i > 0 else None)
                 b["dpre"].append(torch.empty(rows, co, device=dev))
-            F = net.feat_dim
-            b.update(flat=torch.empty(B, F, device=dev), h=torch.empty(B, 256, device=dev), out=torch.empty(B, net.output_dim, device=dev),
-                     dh=torch.empty(B, 256, device=dev), dflat=torch.empty(B, F, device=dev))
+            F, H, c3 = net.feat_dim, self.HID, self.SPECS[2][1]
+            b.update(flat=torch.empty(B, F, device=dev), h=torch.empty(B, H, device=dev), out=torch.empty(B, net.output_dim, device=dev),
+                     dh=torch.empty(B, H, device=dev), dflat=torch.empty(B, F, device=dev))
+            if self.POOL:
+                dp = (dims[3] - self.POOL) // self.POOL + 1
+                b.update(pdim=dp, pooled=torch.empty(B * dp ** 3, c3, device=dev), parg=torch.empty(B * dp ** 3, c3, device=dev, dtype=torch.int32),
+                         dpooled=torch.empty(B * dp ** 3, c3, device=dev))
             self._bufs[B] = b
         return b
 
@@ -277,16 +283,20 @@ class _Conv3DRunner(_Runner):
         src, ld_in, sstride = x, 1, x.stride(0)                      # the TSDF volume: one channel, voxels contiguous per sample
         for i, ((ci, co, k, s), conv) in enumerate(zip(self.SPECS, self._convs())):
             if i == 0:       # one input channel: direct fp32 kernel on the raw volume, no 5 GB patch matrix
-                ops.conv3d_first_forward(x, dims[0], conv.weight.view(co, -1), conv.bias, act, buf["y"][0])
+                ops.conv3d_first_forward(x, dims[0], conv.weight.view(co, -1), conv.bias, act, buf["y"][0], stride=s)
                 src, ld_in, sstride = buf["y"][0], co, dims[1] ** 3 * co
                 continue
             ops.conv3d_im2col(src, ld_in, sstride, B, ci, dims[i], k, s, buf["cols"][i])
             ops.linear_forward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), conv.bias, act, prec, out=buf["y"][i])
             src, ld_in, sstride = buf["y"][i], co, dims[i + 1] ** 3 * co
-        P = dims[3] ** 3
-        ops.conv3d_flatten(buf["y"][2], buf["flat"], B, P, 32, net.feat_dim, True)
+        c3 = self.SPECS[2][1]
+        feat_src, P = buf["y"][2], dims[3] ** 3
+        if self.POOL:                                                # network.py:113: max-pool the encoder output
+            ops.maxpool3d_forward(buf["y"][2], B, c3, dims[3], self.POOL, buf["pooled"], buf["parg"])
+            feat_src, P = buf["pooled"], buf["pdim"] ** 3
+        ops.conv3d_flatten(feat_src, buf["flat"], B, P, c3, net.feat_dim, True)
         if net.proprio_shape:
-            ops.copy_rows(x[:, x.shape[1] - net.proprio_shape:], buf["flat"][:, 32 * P:])
+            ops.copy_rows(x[:, x.shape[1] - net.proprio_shape:], buf["flat"][:, c3 * P:])
         f = net.final_mlp
         ops.linear_forward_tc(buf["flat"], f[0].weight, f[0].bias, act, prec, out=buf["h"])
         return ops.linear_forward_tc(buf["h"], f[2].weight, f[2].bias, None, prec, out=buf["out"])
@@ -298,16 +308,22 @@ class _Conv3DRunner(_Runner):
         buf = self._get(B, x.device)
         dims, act = buf["dims"], net.act_name
         f = net.final_mlp
-        P = dims[3] ** 3
+        c3 = self.SPECS[2][1]
         ops.linear_backward_tc(buf["h"], f[2].weight, dout, grads[8], grads[9], buf["dh"], act, prec)
-        # d flat = (dh W0) * act'(flat): on the encoder columns flat IS act(conv3 pre-activation), so this is dPre3 (flatten order)
-        ops.linear_backward_tc(buf["flat"], f[0].weight, buf["dh"], grads[6], grads[7], buf["dflat"], act, prec)
-        ops.conv3d_flatten(buf["dflat"], buf["dpre"][2], B, P, 32, net.feat_dim, False)
+        if self.POOL:
+            # the pooled features are not an activation output of their own: plain d flat, routed to the winning voxels, times act'(y3)
+            ops.linear_backward_tc(buf["flat"], f[0].weight, buf["dh"], grads[6], grads[7], buf["dflat"], None, prec)
+            ops.conv3d_flatten(buf["dflat"], buf["dpooled"], B, buf["pdim"] ** 3, c3, net.feat_dim, False)
+            ops.maxpool3d_backward(buf["dpooled"], buf["parg"], buf["y"][2], act, B, c3, dims[3], self.POOL, buf["dpre"][2])
+        else:
+            # d flat = (dh W0) * act'(flat): on the encoder columns flat IS act(conv3 pre-activation), so this is dPre3 (flatten order)
+            ops.linear_backward_tc(buf["flat"], f[0].weight, buf["dh"], grads[6], grads[7], buf["dflat"], act, prec)
+            ops.conv3d_flatten(buf["dflat"], buf["dpre"][2], B, dims[3] ** 3, c3, net.feat_dim, False)
         for i in (2, 1, 0):
             ci, co, k, s = self.SPECS[i]
             conv = self._convs()[i]
             if i == 0:
-                ops.conv3d_first_backward(x, dims[0], buf["dpre"][0], grads[0].view(co, -1), grads[1])
+                ops.conv3d_first_backward(x, dims[0], buf["dpre"][0], grads[0].view(co, -1), grads[1], stride=s)
                 continue
             ops.linear_backward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), buf["dpre"][i], grads[2 * i].view(co, -1),
                                    grads[2 * i + 1], buf["dcols"][i][:, :ci * k ** 3] if i > 0 else None, None, prec)
@@ -345,6 +361,42 @@ class Conv3DNet(nn.Module):
         if self.precision not in ("fp32", "bf16"):
             raise NotImplementedError(f"precision {self.precision!r}")
         self.runner = _Conv3DRunner(self)
+
+    def forward(self, x):
+        return _NetFunction.apply(self, x, *self.parameters())
+
+
+class _PoolConv3DRunner(_Conv3DRunner):
+    SPECS = ((1, 16, 5, 2), (16, 32, 3, 2), (32, 64, 3, 2))          # network.py:104
+    POOL = 4                                                         # network.py:106
+    HID = 32
+
+
+class PoolConv3DNet(nn.Module):
+    """network.py:100-117: Encoder(1, [16,32,64], [5,3,3], [2,2,2]) -> MaxPool3d(4) -> Linear(64,32)-act-Linear(32,out).  The reference
+    hard-codes 64 pooled features, i.e. one pooling cell (res 50: 25 -> 13 -> 7 voxels, of which the pool keeps the [0,4)^3 corner); the
+    proprioceptive columns are not used by this network (its forward reshapes the whole row into the volume)."""
+
+    def __init__(self, input_dim, output_dim, net_cfg, proprio_shape):
+        super().__init__()
+        self.res = round(input_dim ** (1 / 3))
+        self.encoder = _Conv3DEncoder(1, [16, 32, 64], [5, 3, 3], [2, 2, 2])
+        self.activation = get_activation(net_cfg['activation'])
+        self.maxpool = nn.MaxPool3d(kernel_size=4)
+        self.final_mlp = nn.Sequential(nn.Linear(64, 32), self.activation, nn.Linear(32, output_dim))
+        self.proprio_shape = 0
+        self.act_name = net_cfg['activation']
+        self.output_dim = output_dim
+        self.feat_dim = 64
+        self.precision = net_cfg.get('precision', 'fp32')
+        if self.precision not in ("fp32", "bf16"):
+            raise NotImplementedError(f"precision {self.precision!r}")
+        d = self.res
+        for _, _, k, s in _PoolConv3DRunner.SPECS:
+            d = ops.conv3d_out_dim(d, k, s)
+        if d < 4 or (d - 4) // 4 + 1 != 1:
+            raise ValueError(f"PoolConv3DNet: resolution {self.res} does not pool to the single cell final_mlp expects")
+        self.runner = _PoolConv3DRunner(self)
 
     def forward(self, x):
         return _NetFunction.apply(self, x, *self.parameters())

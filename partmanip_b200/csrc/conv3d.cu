@@ -93,16 +93,16 @@ flatten3d_kernel(const float* __restrict__ in, float* __restrict__ out, int B, i
 // matrix (5 GB at 2048 samples) against a 16-column weight; done directly instead, in exact fp32 like the reference.
 // A CTA owns one output z-plane of one sample: the five input planes it needs sit in shared memory (zero-padded), the 125 x 16
 // weights too ([tap][channel], read as broadcast float4s); a thread owns output positions and all 16 channels.
-constexpr int C1_OUT = 16, C1_K = 5, C1_S = 3, C1_TAPS = 125, C1_THREADS = 320;
+constexpr int C1_OUT = 16, C1_K = 5, C1_TAPS = 125, C1_THREADS = 320;     // stride S: a kernel argument (3 in Conv3DNet, 2 in PoolConv3DNet)
 
-// slab[kd][y][x] = vol[3*od - 2 + kd][y - 2][x - 2] (0 outside), y, x in [0, W): asynchronous 4-byte copies (cp.async with zero fill) —
+// slab[kd][y][x] = vol[S*od - 2 + kd][y - 2][x - 2] (0 outside), y, x in [0, W): asynchronous 4-byte copies (cp.async with zero fill) —
 // every element's load is in flight at once (a plain load loop serialises on the ~700-cycle miss latency: 40 us per slab measured);
 // one integer division per row, none per element.  The caller waits with conv1_slab_wait().
-__device__ __forceinline__ void conv1_load_slab(float* slab, const float* __restrict__ vol, int Din, int W, int od) {
+__device__ __forceinline__ void conv1_load_slab(float* slab, const float* __restrict__ vol, int Din, int W, int od, int S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int r = warp; r < C1_K * W; r += nwarps) {
     const int kd = r / W, y = r - kd * W;
-    const int id = od * C1_S - 2 + kd, ih = y - 2;
+    const int id = od * S - 2 + kd, ih = y - 2;
     const bool row_ok = id >= 0 && id < Din && ih >= 0 && ih < Din;
     const float* src = vol + ((int64_t)(row_ok ? id : 0) * Din + (row_ok ? ih : 0)) * Din;
     for (int x = lane; x < W; x += 32) {
@@ -117,14 +117,14 @@ __device__ __forceinline__ void conv1_load_slab(float* slab, const float* __rest
 __device__ __forceinline__ void conv1_slab_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(C1_THREADS)
-conv1_fwd_kernel(const float* __restrict__ x, int64_t ldx, int Din, int Dout, const float* __restrict__ w /* (16,125) */,
+conv1_fwd_kernel(const float* __restrict__ x, int64_t ldx, int Din, int Dout, int S, const float* __restrict__ w /* (16,125) */,
                  const float* __restrict__ bias, int act, float* __restrict__ y /* ((b, od, oh, ow), 16) */) {
   extern __shared__ __align__(16) float sm1[];
-  const int W = (Dout - 1) * C1_S + C1_K;
+  const int W = (Dout - 1) * S + C1_K;
   float* slab = sm1;
   float4* wt = reinterpret_cast<float4*>(sm1 + ((C1_K * W * W + 3) / 4 * 4));    // [tap][4 x float4]
   const int od = blockIdx.x, b = blockIdx.y;
-  conv1_load_slab(slab, x + (int64_t)b * ldx, Din, W, od);
+  conv1_load_slab(slab, x + (int64_t)b * ldx, Din, W, od, S);
   for (int i = threadIdx.x; i < C1_TAPS * C1_OUT; i += blockDim.x) {
     const int tap = i / C1_OUT, co = i - tap * C1_OUT;
     reinterpret_cast<float*>(wt)[i] = w[co * C1_TAPS + tap];
@@ -136,7 +136,7 @@ conv1_fwd_kernel(const float* __restrict__ x, int64_t ldx, int Din, int Dout, co
     float acc[C1_OUT];
 #pragma unroll
     for (int c = 0; c < C1_OUT; ++c) acc[c] = bias[c];
-    const float* base = slab + (oh * C1_S) * W + ow * C1_S;
+    const float* base = slab + (oh * S) * W + ow * S;
 #pragma unroll 1
     for (int kd = 0; kd < C1_K; ++kd)
 #pragma unroll
@@ -165,10 +165,10 @@ conv1_fwd_kernel(const float* __restrict__ x, int64_t ldx, int Din, int Dout, co
 // broadcast float4 loads of dpre feed 80 FFMAs.  part[cta][g][tap][16]; the reduce kernel sums ctas and groups in a fixed order.
 constexpr int C1_DW_THREADS = 128, C1_DW_GROUPS = 4;
 __global__ void __launch_bounds__(C1_DW_THREADS)
-conv1_dw_kernel(const float* __restrict__ x, int64_t ldx, int B, int Din, int Dout, const float* __restrict__ dpre /* ((b,od,oh,ow),16) */,
+conv1_dw_kernel(const float* __restrict__ x, int64_t ldx, int B, int Din, int Dout, int S, const float* __restrict__ dpre /* ((b,od,oh,ow),16) */,
                 float* __restrict__ part) {
   extern __shared__ __align__(16) float sm1[];
-  const int W = (Dout - 1) * C1_S + C1_K, P2 = Dout * Dout;
+  const int W = (Dout - 1) * S + C1_K, P2 = Dout * Dout;
   float* slab = sm1;
   float4* dp = reinterpret_cast<float4*>(sm1 + ((C1_K * W * W + 3) / 4 * 4));    // [pos][4 x float4]
   int* off = reinterpret_cast<int*>(dp + P2 * 4);                                // [pos] = (3 oh) W + 3 ow
@@ -179,12 +179,12 @@ conv1_dw_kernel(const float* __restrict__ x, int64_t ldx, int B, int Din, int Do
   for (int kw = 0; kw < C1_K; ++kw)
 #pragma unroll
     for (int c = 0; c < C1_OUT; ++c) acc[kw][c] = 0.f;
-  for (int pos = t; pos < P2; pos += blockDim.x) off[pos] = (pos / Dout) * C1_S * W + (pos % Dout) * C1_S;
+  for (int pos = t; pos < P2; pos += blockDim.x) off[pos] = (pos / Dout) * S * W + (pos % Dout) * S;
   const int64_t pairs = (int64_t)B * Dout;
   for (int64_t pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
     const int b = (int)(pr / Dout), od = (int)(pr - (int64_t)b * Dout);
     __syncthreads();                                                             // previous pair fully consumed
-    conv1_load_slab(slab, x + (int64_t)b * ldx, Din, W, od);
+    conv1_load_slab(slab, x + (int64_t)b * ldx, Din, W, od, S);
     const float4* src = reinterpret_cast<const float4*>(dpre + ((int64_t)b * Dout + od) * P2 * C1_OUT);
     for (int i = t; i < P2 * 4; i += blockDim.x) {
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dp + i);
@@ -231,12 +231,63 @@ conv1_dw_reduce_kernel(const float* __restrict__ part, int n_part, float* __rest
   tsum = pm_warp_sum(tsum);
   if (lane == 0) dW[co * C1_TAPS + tap] = tsum;
 }
-inline size_t conv1_smem_fwd(int Dout) {
-  const int W = (Dout - 1) * C1_S + C1_K;
+// ---------------------------------------------------------------------------------------------------------------- max pooling
+// nn.MaxPool3d(kernel_size = k) (stride k, no padding; network.py:103) on channels-last rows: out[(b, cell), c] = max over the cell's
+// k^3 voxels, scanned in (d, h, w) order with a strict comparison (the first maximum wins, as in torch); arg = that voxel's index in
+// the sample.  Voxels beyond Dp * k (Din not a multiple of k) belong to no cell, exactly as in torch.
+__global__ void __launch_bounds__(256)
+maxpool3d_fwd_kernel(const float* __restrict__ y, int B, int C, int Din, int k, int Dp, float* __restrict__ out, int32_t* __restrict__ arg) {
+  const int64_t total = (int64_t)B * Dp * Dp * Dp * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t cell = i / C;
+    const int pw = (int)(cell % Dp); cell /= Dp;
+    const int ph = (int)(cell % Dp); cell /= Dp;
+    const int pd = (int)(cell % Dp);
+    const int b = (int)(cell / Dp);
+    const float* src = y + (int64_t)b * Din * Din * Din * C + c;
+    float best = -INFINITY;
+    int bi = ((pd * k) * Din + ph * k) * Din + pw * k;
+    for (int d = 0; d < k; ++d)
+      for (int h = 0; h < k; ++h)
+        for (int w = 0; w < k; ++w) {
+          const int v = ((pd * k + d) * Din + ph * k + h) * Din + pw * k + w;
+          const float val = __ldg(src + (int64_t)v * C);
+          if (val > best || val != val) { best = val; bi = v; }
+        }
+    out[i] = best;
+    arg[i] = bi;
+  }
+}
+
+// dpre[(b, voxel), c] = (voxel == arg[(b, cell(voxel)), c] ? dout[(b, cell), c] : 0) * act'(y[(b, voxel), c])
+__global__ void __launch_bounds__(256)
+maxpool3d_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ arg, const float* __restrict__ y, int act, int B, int C, int Din,
+                     int k, int Dp, float* __restrict__ dpre) {
+  const int64_t total = (int64_t)B * Din * Din * Din * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t vox = i / C;
+    const int w = (int)(vox % Din); vox /= Din;
+    const int h = (int)(vox % Din); vox /= Din;
+    const int d = (int)(vox % Din);
+    const int b = (int)(vox / Din);
+    const int pd = d / k, ph = h / k, pw = w / k;
+    float g = 0.f;
+    if (pd < Dp && ph < Dp && pw < Dp) {
+      const int64_t cell = ((((int64_t)b * Dp + pd) * Dp + ph) * Dp + pw) * C + c;
+      if (arg[cell] == (d * Din + h) * Din + w) g = dout[cell] * pm_act_bwd(act, y[i]);
+    }
+    dpre[i] = g;
+  }
+}
+
+inline size_t conv1_smem_fwd(int Dout, int S) {
+  const int W = (Dout - 1) * S + C1_K;
   return ((size_t)(C1_K * W * W + 3) / 4 * 4 + C1_TAPS * C1_OUT) * sizeof(float);
 }
-inline size_t conv1_smem_dw(int Dout) {
-  const int W = (Dout - 1) * C1_S + C1_K;
+inline size_t conv1_smem_dw(int Dout, int S) {
+  const int W = (Dout - 1) * S + C1_K;
   return ((size_t)(C1_K * W * W + 3) / 4 * 4 + Dout * Dout * C1_OUT + Dout * Dout) * sizeof(float);
 }
 constexpr int C1_DW_CTAS = 3 * PM_NUM_SMS;
@@ -277,13 +328,13 @@ int pm_conv3d_col2im(const float* dcols, int Kpad, int B, int C, int Din, int k,
 }
 
 // first layer of the student, Conv3d(1, 16, 5, stride 3, padding 2) + activation, directly on the volume rows x (B, >= Din^3)
-int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, const float* w, const float* bias, int act, float* y,
+int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, int stride, const float* w, const float* bias, int act, float* y,
                             pm_stream_t st) {
-  PM_REQUIRE(x && w && bias && y && B > 0 && B <= 65535 && Din >= 3 && ldx >= (int64_t)Din * Din * Din, PM_ERR_ARG,
-             "pm_conv3d_first_forward: bad arguments (B=%d Din=%d)", B, Din);
+  PM_REQUIRE(x && w && bias && y && B > 0 && B <= 65535 && Din >= 3 && stride >= 1 && ldx >= (int64_t)Din * Din * Din, PM_ERR_ARG,
+             "pm_conv3d_first_forward: bad arguments (B=%d Din=%d stride=%d)", B, Din, stride);
   PM_REQUIRE(act >= PM_ACT_NONE && act <= PM_ACT_SIGMOID, PM_ERR_ARG, "pm_conv3d_first_forward: activation %d", act);
-  const int Dout = pm_conv3d_out_dim(Din, C1_K, C1_S);
-  const size_t smem = conv1_smem_fwd(Dout);
+  const int Dout = pm_conv3d_out_dim(Din, C1_K, stride);
+  const size_t smem = conv1_smem_fwd(Dout, stride);
   PM_REQUIRE(smem <= 227 * 1024, PM_ERR_UNSUPPORTED, "pm_conv3d_first_forward: volume resolution %d needs %zu B of shared memory", Din, smem);
   static size_t attr = 0;
   if (smem > attr) {
@@ -291,7 +342,7 @@ int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, const f
     if (e != cudaSuccess) PM_FAIL(PM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = smem;
   }
-  conv1_fwd_kernel<<<dim3(Dout, B), C1_THREADS, smem, pm_st(st)>>>(x, ldx, Din, Dout, w, bias, act, y);
+  conv1_fwd_kernel<<<dim3(Dout, B), C1_THREADS, smem, pm_st(st)>>>(x, ldx, Din, Dout, stride, w, bias, act, y);
   PM_CHECK_LAUNCH("pm_conv3d_first_forward");
   return PM_OK;
 }
@@ -299,10 +350,10 @@ int pm_conv3d_first_forward(const float* x, int64_t ldx, int B, int Din, const f
 size_t pm_conv3d_first_backward_ws_bytes(void) { return (size_t)C1_DW_CTAS * C1_DW_GROUPS * C1_TAPS * C1_OUT * sizeof(float); }
 
 // dW (16,1,5,5,5) of that layer from dpre ((b, voxel), 16) — no patch matrix; db is a column sum of dpre (pm_rms_colsum et al.)
-int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, const float* dpre, float* dW, void* ws, pm_stream_t st) {
-  PM_REQUIRE(x && dpre && dW && ws && B > 0 && Din >= 3, PM_ERR_ARG, "pm_conv3d_first_backward: bad arguments");
-  const int Dout = pm_conv3d_out_dim(Din, C1_K, C1_S);
-  const size_t smem = conv1_smem_dw(Dout);
+int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, int stride, const float* dpre, float* dW, void* ws, pm_stream_t st) {
+  PM_REQUIRE(x && dpre && dW && ws && B > 0 && Din >= 3 && stride >= 1, PM_ERR_ARG, "pm_conv3d_first_backward: bad arguments");
+  const int Dout = pm_conv3d_out_dim(Din, C1_K, stride);
+  const size_t smem = conv1_smem_dw(Dout, stride);
   PM_REQUIRE(smem <= 227 * 1024, PM_ERR_UNSUPPORTED, "pm_conv3d_first_backward: volume resolution %d needs %zu B of shared memory", Din, smem);
   static size_t attr = 0;
   if (smem > attr) {
@@ -313,7 +364,7 @@ int pm_conv3d_first_backward(const float* x, int64_t ldx, int B, int Din, const 
   float* part = reinterpret_cast<float*>(ws);
   const int64_t pairs = (int64_t)B * Dout;
   const int n_cta = (int)(pairs < C1_DW_CTAS ? pairs : C1_DW_CTAS);
-  conv1_dw_kernel<<<n_cta, C1_DW_THREADS, smem, pm_st(st)>>>(x, ldx, B, Din, Dout, dpre, part);
+  conv1_dw_kernel<<<n_cta, C1_DW_THREADS, smem, pm_st(st)>>>(x, ldx, B, Din, Dout, stride, dpre, part);
   conv1_dw_reduce_kernel<<<pm_cdiv(C1_TAPS * C1_OUT, 8), 256, 0, pm_st(st)>>>(part, n_cta * C1_DW_GROUPS, dW);
   PM_CHECK_LAUNCH("pm_conv3d_first_backward");
   return PM_OK;
@@ -323,6 +374,24 @@ int pm_conv3d_flatten(const float* in, float* out, int B, int P, int C, int64_t 
   PM_REQUIRE(in && out && B > 0 && P > 0 && C > 0 && ld_row >= (int64_t)P * C, PM_ERR_ARG, "pm_conv3d_flatten: bad arguments");
   flatten3d_kernel<<<grid_for((int64_t)B * P * C), 256, 0, pm_st(st)>>>(in, out, B, P, C, ld_row, to_rows);
   PM_CHECK_LAUNCH("pm_conv3d_flatten");
+  return PM_OK;
+}
+
+int pm_maxpool3d_forward(const float* y, int B, int C, int Din, int k, float* out, int32_t* argmax, pm_stream_t st) {
+  PM_REQUIRE(y && out && argmax && B > 0 && C > 0 && k > 0 && Din >= k, PM_ERR_ARG, "pm_maxpool3d_forward: bad arguments (Din=%d k=%d)", Din, k);
+  const int Dp = (Din - k) / k + 1;
+  maxpool3d_fwd_kernel<<<grid_for((int64_t)B * Dp * Dp * Dp * C), 256, 0, pm_st(st)>>>(y, B, C, Din, k, Dp, out, argmax);
+  PM_CHECK_LAUNCH("pm_maxpool3d_forward");
+  return PM_OK;
+}
+
+int pm_maxpool3d_backward(const float* dout, const int32_t* argmax, const float* y, int act, int B, int C, int Din, int k, float* dpre,
+                          pm_stream_t st) {
+  PM_REQUIRE(dout && argmax && y && dpre && B > 0 && C > 0 && k > 0 && Din >= k, PM_ERR_ARG, "pm_maxpool3d_backward: bad arguments");
+  PM_REQUIRE(act >= PM_ACT_NONE && act <= PM_ACT_SIGMOID, PM_ERR_ARG, "pm_maxpool3d_backward: activation %d", act);
+  const int Dp = (Din - k) / k + 1;
+  maxpool3d_bwd_kernel<<<grid_for((int64_t)B * Din * Din * Din * C), 256, 0, pm_st(st)>>>(dout, argmax, y, act, B, C, Din, k, Dp, dpre);
+  PM_CHECK_LAUNCH("pm_maxpool3d_backward");
   return PM_OK;
 }
 

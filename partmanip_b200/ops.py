@@ -517,20 +517,36 @@ def conv3d_col2im(dcols: Tensor, B: int, C: int, Din: int, k: int, s: int, y: Te
     return din
 
 
-def conv3d_first_forward(x: Tensor, Din: int, w: Tensor, bias: Tensor, act, y: Tensor):
-    """Conv3d(1,16,5,stride 3,padding 2) + act on volume rows x (B, >= Din^3) -> y ((b, voxel'), 16), exact fp32."""
+def conv3d_first_forward(x: Tensor, Din: int, w: Tensor, bias: Tensor, act, y: Tensor, stride: int = 3):
+    """Conv3d(1,16,5,stride,padding 2) + act on volume rows x (B, >= Din^3) -> y ((b, voxel'), 16), exact fp32."""
     B, _, ldx = _rows(_f32(x, "x"), "x")
     assert _f32(w, "w").is_contiguous() and w.numel() == 16 * 125 and _f32(y, "y").is_contiguous()
-    check(lib.pm_conv3d_first_forward(_p(x), ldx, B, int(Din), _p(w), _p(bias), PM_ACT[act], _p(y), _stream()), "pm_conv3d_first_forward")
+    check(lib.pm_conv3d_first_forward(_p(x), ldx, B, int(Din), int(stride), _p(w), _p(bias), PM_ACT[act], _p(y), _stream()), "pm_conv3d_first_forward")
     return y
 
 
-def conv3d_first_backward(x: Tensor, Din: int, dpre: Tensor, dW: Tensor, db: Tensor):
+def conv3d_first_backward(x: Tensor, Din: int, dpre: Tensor, dW: Tensor, db: Tensor, stride: int = 3):
     B, _, ldx = _rows(_f32(x, "x"), "x")
     assert _f32(dpre, "dpre").is_contiguous() and dpre.shape[1] == 16 and dW.is_contiguous() and dW.numel() == 16 * 125
     ws = scratch(lib.pm_conv3d_first_backward_ws_bytes(), x.device, "conv1bwd")
-    check(lib.pm_conv3d_first_backward(_p(x), ldx, B, int(Din), _p(dpre), _p(dW), _p(ws), _stream()), "pm_conv3d_first_backward")
+    check(lib.pm_conv3d_first_backward(_p(x), ldx, B, int(Din), int(stride), _p(dpre), _p(dW), _p(ws), _stream()), "pm_conv3d_first_backward")
     rms_colsum(dpre, db)
+
+
+def maxpool3d_forward(y: Tensor, B: int, C: int, Din: int, k: int, out: Tensor, argmax: Tensor):
+    """nn.MaxPool3d(k) on channels-last rows ((b, voxel), C) -> out ((b, cell), C), argmax int32."""
+    Dp = (Din - k) // k + 1
+    assert _f32(y, "y").is_contiguous() and y.shape == (B * Din ** 3, C) and _f32(out, "out").is_contiguous() and out.shape == (B * Dp ** 3, C)
+    assert argmax.dtype == torch.int32 and argmax.is_contiguous() and argmax.shape == out.shape and argmax.is_cuda
+    check(lib.pm_maxpool3d_forward(_p(y), B, C, int(Din), int(k), _p(out), _p(argmax), _stream()), "pm_maxpool3d_forward")
+    return out
+
+
+def maxpool3d_backward(dout: Tensor, argmax: Tensor, y: Tensor, act, B: int, C: int, Din: int, k: int, dpre: Tensor):
+    assert _f32(dout, "dout").is_contiguous() and dout.shape == argmax.shape and _f32(dpre, "dpre").is_contiguous() and dpre.shape == y.shape
+    check(lib.pm_maxpool3d_backward(_p(dout), _p(argmax), _p(_f32(y, "y")), PM_ACT[act], B, C, int(Din), int(k), _p(dpre), _stream()),
+          "pm_maxpool3d_backward")
+    return dpre
 
 
 def conv3d_flatten(src: Tensor, dst: Tensor, B: int, P: int, C: int, ld_row: int, to_rows: bool):

@@ -147,3 +147,70 @@ def test_dagger_update_with_the_conv3d_student_vs_oracle(tmp_path):
         d = (got[k] - v).abs()
         # Adam's first step moves every weight by ~lr * sign(g): elements whose gradient is within rounding of 0 may differ by up to 2 lr
         assert float((d > 0.05 * 1e-4).float().mean()) <= 0.02 and float(d.max()) <= 2.1e-4, (k, float((d > 5e-6).float().mean()), float(d.max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------- PoolConv3DNet
+GP = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poolconv3d_student.npz"))
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("tag", ["tanh", "relu"])
+def test_poolconv3dnet_matches_the_reference_recording(tag, precision, rtol):
+    """network.py:100-117 (stride-2 encoder, MaxPool3d(4) that keeps the [0,4)^3 corner of the 7^3 map, 64 -> 32 -> out head) against the
+    recording of the unmodified module: outputs and every parameter gradient."""
+    from partmanip_b200.algorithms.algo_utils.network import PoolConv3DNet
+    params = {k[len(tag) + 7:]: GP[k] for k in GP.files if k.startswith(tag + "_param_")}
+    want_grads = {k[len(tag) + 6:]: GP[k] for k in GP.files if k.startswith(tag + "_grad_")}
+    x, want_y, gy = GP[tag + "_x"], GP[tag + "_y"], GP[tag + "_gy"]
+    net = PoolConv3DNet(x.shape[1], 10, dict(name="PoolConv3DNet", activation=tag, precision=precision), 0)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in params.items()})
+    net.to(DEV)
+    assert [k for k, _ in net.named_parameters()] == list(params)
+    y = net(torch.from_numpy(x).to(DEV))
+    got = y.detach().cpu().numpy()
+    assert float(np.abs(got - want_y).max()) <= rtol + rtol * float(np.abs(want_y).max()), float(np.abs(got - want_y).max())
+    (y * torch.from_numpy(gy).to(DEV)).sum().backward()
+    for k, p in net.named_parameters():
+        g, w = p.grad.cpu().numpy(), want_grads[k]
+        assert g.shape == w.shape and np.isfinite(g).all(), k
+        if precision == "fp32":
+            tol = rtol * max(1e-3, float(np.abs(w).max()))
+            assert float(np.abs(g - w).max()) <= tol, (k, float(np.abs(g - w).max()), tol)
+        else:       # bf16 operands: a pooled maximum may move to a neighbouring voxel; relative L2 per tensor
+            rel = float(np.linalg.norm(g - w) / (np.linalg.norm(w) + 1e-12))
+            assert rel <= 2e-1, (k, rel)
+
+
+def test_maxpool3d_vs_torch():
+    """pm_maxpool3d_forward / _backward against nn.MaxPool3d + autograd: ties (first maximum wins), a resolution that is not a multiple of
+    the kernel (the tail voxels belong to no cell and get zero gradient), several cells per axis."""
+    from partmanip_b200 import ops
+    torch.manual_seed(0)
+    B, C, Din, k = 3, 5, 9, 4                                      # Dp = 2: voxels 8 of each axis are dropped
+    y = torch.randn(B, C, Din, Din, Din)
+    y[0, 0, :4, :4, :4] = 1.5                                      # a whole cell tied
+    y[1, 2, 4:8, 0:4, 4:8] = torch.round(y[1, 2, 4:8, 0:4, 4:8])   # many ties
+    yr = torch.tanh(y).requires_grad_(True)                        # the pooled tensor is an activation output
+    pooled = torch.nn.functional.max_pool3d(yr, k)
+    dout = torch.randn_like(pooled)
+    (gy,) = torch.autograd.grad(pooled, yr, dout)
+    want_dpre = gy * (1 - yr.detach() ** 2)                        # times tanh' expressed through the output
+    rows = yr.detach().permute(0, 2, 3, 4, 1).reshape(-1, C).contiguous().to(DEV)
+    Dp = (Din - k) // k + 1
+    out = torch.empty(B * Dp ** 3, C, device=DEV)
+    arg = torch.empty(B * Dp ** 3, C, device=DEV, dtype=torch.int32)
+    ops.maxpool3d_forward(rows, B, C, Din, k, out, arg)
+    assert torch.equal(out.cpu(), pooled.detach().permute(0, 2, 3, 4, 1).reshape(-1, C))
+    dpre = torch.full_like(rows, float("nan"))
+    ops.maxpool3d_backward(dout.permute(0, 2, 3, 4, 1).reshape(-1, C).contiguous().to(DEV), arg, rows, "tanh", B, C, Din, k, dpre)
+    want = want_dpre.permute(0, 2, 3, 4, 1).reshape(-1, C)
+    assert float((dpre.cpu() - want).abs().max()) <= 1e-6
+
+
+def test_actor_critic_resolves_poolconv3dnet():
+    from partmanip_b200.algorithms.algo_utils import ActorCritic
+    ac = ActorCritic(50 ** 3, 7, dict(action_std=0.5, action_activate="tanh", clipAction=1.0, network=dict(name="PoolConv3DNet", activation="tanh")), 0).to(DEV)
+    x = torch.rand(2, 50 ** 3, device=DEV) * 2 - 1
+    a = ac.act(x)
+    v = ac.cri(x)
+    assert a.shape == (2, 7) and v.shape == (2, 1) and bool(torch.isfinite(a).all()) and float(a.abs().max()) <= 1.0
