@@ -346,16 +346,19 @@ int pm_tsdf_sparse_voxel(const float* tsdf /* (E,R,R,R) */, int E, int resolutio
  * NEXT ROW (second half): the Conv3D student on the fused TSDF volume — algorithms/algo_utils/network.py:56-63
  * (conv_stride = nn.Conv3d(stride, padding = k // 2)), :67-97 (Conv3DNet), :119-135 (Encoder).  A convolution = pm_conv3d_im2col
  * + pm_linear_forward_tc (bias + activation fused) on CHANNELS-LAST activations ((sample, voxel) rows x channels); its backward =
- * pm_linear_backward_tc + pm_conv3d_col2im.  The patch column order (c, kd, kh, kw) is nn.Conv3d's weight.view(Cout, -1) order.
+ * pm_linear_backward_tc + pm_conv3d_col2im.  The patch column order is TAP-major, (kd, kh, kw, c): a tap's channels are contiguous in
+ * the activations and in the patch row (16-byte vector moves when C % 4 == 0); pm_conv3d_weight_permute brings nn.Conv3d's
+ * weight.view(Cout, C, k^3) into that order (to_tap_major != 0) and a weight gradient back (to_tap_major == 0).
  * ------------------------------------------------------------------------------------------ */
 int pm_conv3d_out_dim(int Din, int k, int s);
-/* cols[(b, od, oh, ow), (c, kd, kh, kw)] = in[b*sample_stride + voxel*ld_in + c] (0 outside the volume); row stride Kpad >= C*k^3,
+/* cols[(b, od, oh, ow), (kd, kh, kw, c)] = in[b*sample_stride + voxel*ld_in + c] (0 outside the volume); row stride Kpad >= C*k^3,
  * padding columns zeroed.  in: voxel (id, ih, iw) of sample b at in + b*sample_stride + ((id*Din + ih)*Din + iw)*ld_in. */
 int pm_conv3d_im2col(const float* in, int64_t ld_in, int64_t sample_stride, int B, int C, int Din, int k, int s, float* cols, int Kpad,
                      pm_stream_t st);
 /* adjoint of im2col in gather form (deterministic), times act'(y): din[(b, voxel), c] = (sum of covering patch entries) * act'(y[...]) */
 int pm_conv3d_col2im(const float* dcols, int Kpad, int B, int C, int Din, int k, int s, const float* y, int act, float* din,
                      pm_stream_t st);
+int pm_conv3d_weight_permute(const float* src, int Cout, int C, int k, int to_tap_major, float* dst, pm_stream_t st);
 /* The first layer, Conv3d(1, 16, k 5, stride `stride`, padding 2) + activation (network.py:70, 104, 122), directly on the volume rows
  * x (B, >= Din^3) in exact fp32 — no patch matrix (it would be 5 GB at 2048 samples): y ((b, voxel'), 16) channels-last.
  * pm_conv3d_first_backward: dW (16,1,5,5,5) from dpre ((b, voxel'), 16); its bias gradient is a column sum of dpre. */

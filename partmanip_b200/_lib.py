@@ -87,6 +87,7 @@ SIGNATURES = {
     "pm_conv3d_first_forward": (I, [P, L, I, I, I, P, P, I, P, P]),
     "pm_conv3d_first_backward_ws_bytes": (SZ, []),
     "pm_conv3d_first_backward": (I, [P, L, I, I, I, P, P, P, P]),
+    "pm_conv3d_weight_permute": (I, [P, I, I, I, I, P, P]),
     "pm_maxpool3d_forward": (I, [P, I, I, I, I, P, P, P]),
     "pm_maxpool3d_backward": (I, [P, P, P, I, I, I, I, I, P, P]),
     "pm_mesh2sdf_query": (I, [P, L, P, P, P, I, I, I, P, P, P, I, I, C.POINTER(F), F, P, P]),

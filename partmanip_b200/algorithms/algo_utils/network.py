@@ -261,6 +261,9 @@ class _Conv3DRunner(_Runner):
                 b["y"].append(torch.empty(rows, co, device=dev))
                 b["dcols"].append(torch.empty(rows, kpad, device=dev) if i > 0 else None)
                 b["dpre"].append(torch.empty(rows, co, device=dev))
+            # conv2 / conv3 weights (and their gradients) in the tap-major order of the patch columns
+            b["wp"] = [None] + [torch.empty(co, ci * k ** 3, device=dev) for ci, co, k, _ in self.SPECS[1:]]
+            b["dwp"] = [None] + [torch.empty(co, ci * k ** 3, device=dev) for ci, co, k, _ in self.SPECS[1:]]
             F, H, c3 = net.feat_dim, self.HID, self.SPECS[2][1]
             b.update(flat=torch.empty(B, F, device=dev), h=torch.empty(B, H, device=dev), out=torch.empty(B, net.output_dim, device=dev),
                      dh=torch.empty(B, H, device=dev), dflat=torch.empty(B, F, device=dev))
@@ -287,7 +290,8 @@ class _Conv3DRunner(_Runner):
                 src, ld_in, sstride = buf["y"][0], co, dims[1] ** 3 * co
                 continue
             ops.conv3d_im2col(src, ld_in, sstride, B, ci, dims[i], k, s, buf["cols"][i])
-            ops.linear_forward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), conv.bias, act, prec, out=buf["y"][i])
+            ops.conv3d_weight_permute(conv.weight, co, ci, k, True, buf["wp"][i])
+            ops.linear_forward_tc(buf["cols"][i][:, :ci * k ** 3], buf["wp"][i], conv.bias, act, prec, out=buf["y"][i])
             src, ld_in, sstride = buf["y"][i], co, dims[i + 1] ** 3 * co
         c3 = self.SPECS[2][1]
         feat_src, P = buf["y"][2], dims[3] ** 3
@@ -325,8 +329,9 @@ class _Conv3DRunner(_Runner):
             if i == 0:
                 ops.conv3d_first_backward(x, dims[0], buf["dpre"][0], grads[0].view(co, -1), grads[1], stride=s)
                 continue
-            ops.linear_backward_tc(buf["cols"][i][:, :ci * k ** 3], conv.weight.view(co, -1), buf["dpre"][i], grads[2 * i].view(co, -1),
+            ops.linear_backward_tc(buf["cols"][i][:, :ci * k ** 3], buf["wp"][i], buf["dpre"][i], buf["dwp"][i],
                                    grads[2 * i + 1], buf["dcols"][i][:, :ci * k ** 3] if i > 0 else None, None, prec)
+            ops.conv3d_weight_permute(buf["dwp"][i], co, ci, k, False, grads[2 * i])
             if i > 0:
                 ops.conv3d_col2im(buf["dcols"][i], B, ci, dims[i], k, s, buf["y"][i - 1], act, buf["dpre"][i - 1])
 

@@ -504,7 +504,8 @@ def conv3d_out_dim(Din: int, k: int, s: int) -> int:
 
 
 def conv3d_im2col(src: Tensor, ld_in: int, sample_stride: int, B: int, C: int, Din: int, k: int, s: int, cols: Tensor):
-    """network.py:56-63 patches: src holds voxel (d,h,w) of sample b at b*sample_stride + ((d*Din+h)*Din+w)*ld_in + c."""
+    """network.py:56-63 patches in TAP-major column order (kd, kh, kw, c): src holds voxel (d,h,w) of sample b at
+    b*sample_stride + ((d*Din+h)*Din+w)*ld_in + c."""
     assert _f32(src, "src").is_cuda and _f32(cols, "cols").is_contiguous() and cols.dim() == 2
     check(lib.pm_conv3d_im2col(_p(src), int(ld_in), int(sample_stride), B, C, Din, k, s, _p(cols), cols.shape[1], _stream()),
           "pm_conv3d_im2col")
@@ -515,6 +516,13 @@ def conv3d_col2im(dcols: Tensor, B: int, C: int, Din: int, k: int, s: int, y: Te
     assert _f32(dcols, "dcols").is_contiguous() and _f32(y, "y").is_contiguous() and _f32(din, "din").is_contiguous()
     check(lib.pm_conv3d_col2im(_p(dcols), dcols.shape[1], B, C, Din, k, s, _p(y), PM_ACT[act], _p(din), _stream()), "pm_conv3d_col2im")
     return din
+
+
+def conv3d_weight_permute(src: Tensor, Cout: int, C: int, k: int, to_tap_major: bool, dst: Tensor):
+    """nn.Conv3d weight (Cout, C, k^3) <-> the tap-major patch order (Cout, k^3, C) of conv3d_im2col."""
+    assert _f32(src, "src").is_contiguous() and _f32(dst, "dst").is_contiguous() and src.numel() == dst.numel() == Cout * C * k ** 3
+    check(lib.pm_conv3d_weight_permute(_p(src), Cout, C, k, int(to_tap_major), _p(dst), _stream()), "pm_conv3d_weight_permute")
+    return dst
 
 
 def conv3d_first_forward(x: Tensor, Din: int, w: Tensor, bias: Tensor, act, y: Tensor, stride: int = 3):

@@ -85,7 +85,11 @@ def test_conv3d_patch_gather_and_its_adjoint():
         kpad = (K + 3) // 4 * 4
         cols = torch.full((B * Do ** 3, kpad), float("nan"), device=DEV)
         ops.conv3d_im2col(xcl, Cin, Din ** 3 * Cin, B, Cin, Din, k, s, cols)
-        assert np.array_equal(cols[:, :K].cpu().numpy(), want.reshape(-1, K)) and bool((cols[:, K:] == 0).all())
+        want_tm = want.reshape(-1, Cin, k ** 3).transpose(0, 2, 1).reshape(-1, K)     # the kernels' tap-major column order (kd, kh, kw, c)
+        assert np.array_equal(cols[:, :K].cpu().numpy(), want_tm) and bool((cols[:, K:] == 0).all())
+        w = torch.from_numpy(rng.standard_normal((5, Cin, k ** 3)).astype(np.float32)).to(DEV)
+        wp = ops.conv3d_weight_permute(w, 5, Cin, k, True, torch.empty(5, k ** 3 * Cin, device=DEV))
+        assert torch.equal(wp.view(5, k ** 3, Cin), w.permute(0, 2, 1)) and torch.equal(ops.conv3d_weight_permute(wp, 5, Cin, k, False, torch.empty_like(w)), w)
         g = torch.from_numpy(rng.standard_normal((B * Do ** 3, kpad)).astype(np.float32)).to(DEV)
         din = torch.empty(B * Din ** 3, Cin, device=DEV)
         ops.conv3d_col2im(g, B, Cin, Din, k, s, torch.zeros_like(din), None, din)        # act = none: derivative 1
