@@ -16,7 +16,10 @@
 //    wide): correct, 5.9 ms forward / 4.4 ms weight gradient — with one input channel every gathered element feeds only 16
 //    multiply-adds, which does not pay for its index arithmetic, split into bf16 terms and shared-memory image store;
 //  * the weights in constant memory (FFMA with uniform-register operands, one shared load per tap): correct, 3.3 ms — the uniform
-//    datapath has to deliver a fresh operand for every FFMA and becomes the limiter.
+//    datapath has to deliver a fresh operand for every FFMA and becomes the limiter;
+//  * two output positions per thread (each broadcast weight vector feeds 8 FFMAs, 160-thread CTAs): 2.6 ms; eight instead of four
+//    position groups in conv1_dw_kernel (256 threads): unchanged.  ncu on the kept kernels: forward LSU data pipe 84 % of peak
+//    (shared-memory wavefronts), weight gradient 18 % warp occupancy at 43 % l1tex throughput.
 #include "common.cuh"
 
 namespace {
