@@ -716,14 +716,21 @@ class OpenDrawerPostPlan:
             t = out[k]
             assert t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp, k
             assert t.dtype == (torch.bool if k in ("success", "extras_b") else torch.float32), k
+        # the tensors whose addresses are baked into the argument list (kept alive; `bound_to` tells a caller whether to re-plan)
         self._keep = (dof_state_all, rigid_body_all, root_tensor, dof_state_mask, rigid_body_mask, dof_lower, dof_upper, part_bbox_init, part_axis_dir_init,
                       part_joint_lower, part_joint_upper, obj_lstid, progress_buf, succ_objid, out)
+        self._bound = dict(dof_state_all=dof_state_all, rigid_body_all=rigid_body_all, root_tensor=root_tensor, progress_buf=progress_buf,
+                           succ_objid=succ_objid)
         self._head = (_p(dof_state_all), _p(rigid_body_all), _p(root_tensor), root_tensor.shape[1], int(obj_actor), _p(dof_state_mask), _p(rigid_body_mask),
                       E, nd, nb, int(ltip_rb_index), int(rtip_rb_index), _p(dof_lower), _p(dof_upper), _p(part_bbox_init), _p(part_axis_dir_init),
                       _p(part_joint_lower), _p(part_joint_upper), _p(obj_lstid), float(suc_prop))
         self._tail = (_p(progress_buf), _p(out["obs"]), _p(out["part_bbox"]), _p(out["dof_state_tensor"]), _p(out["rigid_body_tensor"]),
                       _p(out["tip_rb_tensor"]), _p(out["tip_rot_9d"]), _p(out["gripper_length"]), _p(out["dof_qpos_normalized"]), _p(out["rew_buf"]),
                       _p(out["success"]), _p(succ_objid), _p(out["extras_f"]), _p(out["extras_b"]))
+
+    def bound_to(self, **tensors) -> bool:
+        """True if every named tensor is the very object this plan was built on."""
+        return all(self._bound[k] is t for k, t in tensors.items())
 
     def __call__(self, do_obs: bool = True, do_reward: bool = True, advance_progress: bool = False) -> None:
         check(lib.pm_open_drawer_post_physics(*self._head, int(do_obs), int(do_reward), int(advance_progress), *self._tail, _stream()),
@@ -751,11 +758,15 @@ class GraspCubePostPlan:
             assert t.dtype == (torch.bool if k in ("success", "extras_b") else torch.float32), k
         arr = lambda v, n: (ct.c_float * n)(*[float(x) for x in v])
         self._keep = (dof_state, rigid_body, root_tensor, dof_lower, dof_upper, progress_buf, out)
+        self._bound = dict(dof_state=dof_state, rigid_body=rigid_body, root_tensor=root_tensor, progress_buf=progress_buf)
         self._head = (_p(dof_state), dof_state.shape[1], _p(rigid_body), rigid_body.shape[1], _p(root_tensor), root_tensor.shape[1], int(obj_actor), E, nd,
                       int(ltip_rb_index), int(rtip_rb_index), _p(dof_lower), _p(dof_upper), arr(pose_lower_limit, 7), arr(pose_upper_limit, 7),
                       arr(success_pos, 3), arr(obj_default_pos, 3), float(goal_thresh))
         self._tail = (_p(progress_buf), _p(out["obs"]), _p(out["proprio"]), _p(out["tip_rb_tensor"]), _p(out["tip_rot_9d"]), _p(out["gripper_length"]),
                       _p(out["dof_qpos_normalized"]), _p(out["rew_buf"]), _p(out["success"]), _p(out["extras_f"]), _p(out["extras_b"]))
+
+    def bound_to(self, **tensors) -> bool:
+        return all(self._bound[k] is t for k, t in tensors.items())
 
     def __call__(self, do_obs: bool = True, do_reward: bool = True, advance_progress: bool = False) -> None:
         check(lib.pm_grasp_cube_post_physics(*self._head, int(do_obs), int(do_reward), int(advance_progress), *self._tail, _stream()),

@@ -122,7 +122,8 @@ class OpenDrawerKernels(BaseTaskKernels):
     def _pm_launch(self, do_obs, do_reward, advance):
         out = self._pm_buffers()
         plan = getattr(self, "_pm_plan", None)
-        if plan is None or plan._keep[12] is not self.progress_buf or plan._keep[13] is not self.succ_objid_lst:
+        if plan is None or not plan.bound_to(dof_state_all=self.dof_state_tensor_all, rigid_body_all=self.rigid_body_tensor_all,
+                                             root_tensor=self.root_tensor, progress_buf=self.progress_buf, succ_objid=self.succ_objid_lst):
             c, rob = self._pm_const, self.robot
             plan = self._pm_plan = ops.OpenDrawerPostPlan(
                 self.dof_state_tensor_all, self.rigid_body_tensor_all, self.root_tensor, self.obj_actor, c["dof_mask"], c["rb_mask"], rob.ltip_rb_index,
@@ -189,7 +190,8 @@ class GraspCubeKernels(BaseTaskKernels):
     def _pm_launch(self, do_obs, do_reward, advance):
         out = self._pm_buffers()
         plan = getattr(self, "_pm_plan", None)
-        if plan is None or plan._keep[5] is not self.progress_buf:
+        if plan is None or not plan.bound_to(dof_state=self.dof_state_tensor, rigid_body=self.rigid_body_tensor, root_tensor=self.root_tensor,
+                                             progress_buf=self.progress_buf):
             rob = self.robot
             plan = self._pm_plan = ops.GraspCubePostPlan(
                 self.dof_state_tensor, self.rigid_body_tensor, self.root_tensor, self.obj_actor, rob.num_dofs, rob.ltip_rb_index, rob.rtip_rb_index,
