@@ -273,6 +273,9 @@ crit_scan_kernel(const int32_t* __restrict__ ucount, int B, int32_t* __restrict_
 
 // pass 3: per cloud, rank its critical points (ascending point index), list each row's channels
 // (ascending channel index — keeps every later summation order deterministic) and gather the inputs.
+// A channel's place inside its point's segment is the number of lower channels that chose the same point, counted directly
+// (512 broadcast reads per thread) — no atomics on the fill order and no per-segment sort (the earlier version insertion-sorted
+// every segment in global memory, one thread per point: 120 us per minibatch, most of it the long segments' dependent loads).
 __global__ void __launch_bounds__(256)
 crit_fill_kernel(const float* __restrict__ x, int64_t ldx, int N, int C, const int32_t* __restrict__ argmax,
                  int all_points, const int32_t* __restrict__ rowoff, int32_t* __restrict__ row_b,
@@ -282,34 +285,40 @@ crit_fill_kernel(const float* __restrict__ x, int64_t ldx, int N, int C, const i
   int* cnt = sm;            // [N] channels per point
   int* rank = sm + N;       // [N] row rank of point
   int* cbeg = sm + 2 * N;   // [N] start of the point's channel segment
-  int* fill = sm + 3 * N;   // [N]
-  __shared__ int s_carry_r, s_carry_c;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int n = tid; n < N; n += blockDim.x) { cnt[n] = 0; fill[n] = 0; }
-  if (tid == 0) { s_carry_r = 0; s_carry_c = 0; }
+  int* am = sm + 3 * N;     // [512] this cloud's argmax row
+  __shared__ int wsum_r[8], wsum_c[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int n = tid; n < N; n += blockDim.x) cnt[n] = 0;
+  for (int c = tid; c < 512; c += blockDim.x) am[c] = argmax[(int64_t)b * 512 + c];
   __syncthreads();
-  for (int c = tid; c < 512; c += blockDim.x) atomicAdd(&cnt[argmax[(int64_t)b * 512 + c]], 1);
+  for (int c = tid; c < 512; c += blockDim.x) atomicAdd(&cnt[am[c]], 1);      // counts only: the order of the adds is irrelevant
   __syncthreads();
-  // exclusive scans over n (flags -> rank, counts -> cbeg); serial over 256-wide chunks, Hillis-Steele inside
-  __shared__ int sa[256], sb[256];
-  for (int base = 0; base < N; base += 256) {
-    const int n = base + tid;
-    const int f = (n < N) ? ((all_points || cnt[n] > 0) ? 1 : 0) : 0;
-    const int q = (n < N) ? cnt[n] : 0;
-    sa[tid] = f; sb[tid] = q;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {
-      const int ta = (tid >= o) ? sa[tid - o] : 0;
-      const int tb = (tid >= o) ? sb[tid - o] : 0;
-      __syncthreads();
-      sa[tid] += ta; sb[tid] += tb;
-      __syncthreads();
-    }
-    if (n < N) { rank[n] = s_carry_r + sa[tid] - f; cbeg[n] = s_carry_c + sb[tid] - q; }
-    __syncthreads();
-    if (tid == 0) { s_carry_r += sa[255]; s_carry_c += sb[255]; }
-    __syncthreads();
+  // exclusive scans over n of (point is live, channels of the point): each thread owns a run of consecutive points
+  const int per = (N + 255) / 256;
+  const int n0 = tid * per;
+  int fr = 0, fc = 0;
+  for (int i = 0; i < per; ++i) {
+    const int n = n0 + i;
+    if (n < N) { fr += (all_points || cnt[n] > 0) ? 1 : 0; fc += cnt[n]; }
   }
+  int ir = fr, ic = fc;                                                       // inclusive warp scans of the thread totals
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tr = __shfl_up_sync(0xffffffffu, ir, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+    if (lane >= o) { ir += tr; ic += tc; }
+  }
+  if (lane == 31) { wsum_r[warp] = ir; wsum_c[warp] = ic; }
+  __syncthreads();
+  int base_r = ir - fr, base_c = ic - fc;
+  for (int w = 0; w < warp; ++w) { base_r += wsum_r[w]; base_c += wsum_c[w]; }
+  for (int i = 0; i < per; ++i) {
+    const int n = n0 + i;
+    if (n < N) {
+      rank[n] = base_r; cbeg[n] = base_c;
+      base_r += (all_points || cnt[n] > 0) ? 1 : 0; base_c += cnt[n];
+    }
+  }
+  __syncthreads();
   const int r0 = rowoff[b];
   for (int n = tid; n < N; n += blockDim.x) {
     if (all_points || cnt[n] > 0) {
@@ -321,24 +330,11 @@ crit_fill_kernel(const float* __restrict__ x, int64_t ldx, int N, int C, const i
     }
   }
   for (int c = tid; c < 512; c += blockDim.x) {
-    const int n = argmax[(int64_t)b * 512 + c];
-    const int pos = atomicAdd(&fill[n], 1);
+    const int n = am[c];
+    int pos = 0;
+    for (int c2 = 0; c2 < c; ++c2) pos += (am[c2] == n) ? 1 : 0;              // warp-uniform address: a broadcast read
     chan_sorted[b * 512 + cbeg[n] + pos] = c;
     slot[b * 512 + c] = r0 + rank[n];
-  }
-  __syncthreads();
-  __threadfence_block();
-  for (int n = tid; n < N; n += blockDim.x) {   // insertion-sort each (short) segment
-    const int q = cnt[n];
-    if (q > 1) {
-      int32_t* seg = chan_sorted + b * 512 + cbeg[n];
-      for (int i = 1; i < q; ++i) {
-        const int v = seg[i];
-        int j = i - 1;
-        while (j >= 0 && seg[j] > v) { seg[j + 1] = seg[j]; --j; }
-        seg[j + 1] = v;
-      }
-    }
   }
 }
 
@@ -650,7 +646,7 @@ int pm_pointnet_encode_backward(const float* x, int64_t ldx, int B, int N, int C
   // 1. compact the critical points
   crit_count_kernel<<<B, 256, (size_t)N * 4, st>>>(argmax, N, with_mean, w.ucount);
   crit_scan_kernel<<<1, 1024, 0, st>>>(w.ucount, B, w.rowoff, w.r_dev);
-  crit_fill_kernel<<<B, 256, (size_t)N * 16, st>>>(x, ldx, N, C, argmax, with_mean, w.rowoff, w.row_b, w.row_cbeg,
+  crit_fill_kernel<<<B, 256, (size_t)N * 12 + 2048, st>>>(x, ldx, N, C, argmax, with_mean, w.rowoff, w.row_b, w.row_cbeg,
                                                    w.row_ccnt, w.chan_sorted, w.slot, w.Xc);
   // 2. recompute their activations
   const int grid_rows = 8 * PM_NUM_SMS;
