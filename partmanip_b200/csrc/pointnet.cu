@@ -360,7 +360,7 @@ crit_layer1_kernel(const float* __restrict__ Xc, int C, const float* __restrict_
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int r = r0 + u * stride;
-      if (r < R) H1c[(int64_t)r * 128 + ch] = pm_act_fwd(act, a[u]);
+      if (r < R) H1c[(int64_t)r * 128 + ch] = pm_act_fwd_fast(act, a[u]);
     }
   }
 }
