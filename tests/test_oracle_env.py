@@ -82,3 +82,48 @@ def test_grasp_cube_bit_exact():
     a = EO.control(g["actions"], "ik", False, o["robot"]["dof_qpos_raw"], 1 / 60, None, g["in_dof_lower"], g["in_dof_upper"], g["in_jac"],
                    int(g["in_ltip"]), int(g["in_rtip"]))
     assert torch.equal(a, g["action_tensor_ik_fixed"])
+
+
+def test_deambiguity_rotation_properties():
+    """Size-independent properties of utils/torch_jit_utils.py:412-425 as restated: the result is one of the 24 candidate frames built
+    from R's columns, it is orthonormal with det +1 for a unit quaternion, and no other candidate is closer to the identity."""
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(257, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    q[0] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+    out = EO.deambiguity_rotation(q)
+    eye = torch.eye(3).expand_as(out)
+    assert float((out.transpose(-1, -2) @ out - eye).abs().max()) < 1e-5
+    assert float((torch.linalg.det(out) - 1).abs().max()) < 1e-5
+    R = EO.quat_to_mat(q)
+    tr = out.diagonal(dim1=-2, dim2=-1).sum(-1)
+    # every signed column permutation of R that is a proper rotation obtained by the reference's construction has trace <= the winner's
+    ind = [(0, 1), (0, 2), (1, 2), (1, 0), (2, 0), (2, 1)]
+    best = torch.full((q.shape[0],), -10.0)
+    for k in range(24):
+        a, b = R[:, :, ind[k % 6][0]].clone(), R[:, :, ind[k % 6][1]].clone()
+        if k < 12:
+            a[:, 0], b[:, 0] = -a[:, 0], -b[:, 0]
+        if 6 <= k < 18:
+            a[:, 1], b[:, 1] = -a[:, 1], -b[:, 1]
+        c = torch.cross(a, b, dim=-1)
+        best = torch.maximum(best, a[:, 0] + b[:, 1] + c[:, 2])
+    assert float((tr - best).abs().max()) < 1e-5
+    assert torch.allclose(out[0], torch.eye(3), atol=1e-6)                  # the identity stays the identity
+
+
+def test_episode_flags_properties():
+    """hand_base.py:367-377: an env resets iff it stalled for explore_step steps since its best reward or succeeded; the best-reward
+    step only moves when the reward does not fall below the record."""
+    g = torch.Generator().manual_seed(4)
+    E = 1000
+    rew, best = torch.randn(E, generator=g), torch.randn(E, generator=g)
+    prog, step = torch.randint(0, 200, (E,), generator=g), torch.randint(0, 200, (E,), generator=g)
+    succ = torch.rand(E, generator=g) < 0.1
+    f = EO.episode_flags("train", rew, prog, succ, best, step, 40, 200)
+    improved = ~(rew < best)
+    assert torch.equal(f["epis_max_step"][improved], prog[improved]) and torch.equal(f["epis_max_step"][~improved], step[~improved])
+    assert torch.equal(f["epis_max_rew"], torch.maximum(rew, best))
+    assert bool(f["reset_buf"][succ].all()) and bool((f["reset_buf"] == ((prog >= f["epis_max_step"] + 40) | succ)).all())
+    assert abs(float(f["succ_rate"]) - float(succ.sum()) / max(1, int(f["reset_buf"].sum()))) < 1e-7
+    assert torch.equal(EO.episode_flags("test", rew, prog, succ, best, step, 40, 150)["reset_buf"], prog >= 150)
