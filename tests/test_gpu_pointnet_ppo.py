@@ -382,3 +382,36 @@ def test_cuda_graph_update_is_bit_identical_to_eager():
             assert torch.equal(out[0][0][k], out[1][0][k]), k
         for k in ("Train/surrogate_loss", "Train/value_function_loss", "Train/kl", "Train/kl_update_count"):
             assert float(out[0][1][k]) == float(out[1][1][k]) or (out[0][1][k] != out[0][1][k]), k
+
+
+@pytest.mark.parametrize("schedule", ["linear_decay", "step_decay"])
+def test_lr_schedule_reaches_the_replayed_graph(schedule):
+    """ppo.py:390-400: the actor's learning rate changes after every update.  It is a device scalar, so the captured update graph must
+    pick the new value up: four iterations replayed from the graph equal four eager iterations bit for bit, the logged rate follows the
+    reference's formula, and the critic's rate never moves."""
+    from partmanip_b200.algorithms import ppo
+    from partmanip_b200.envs import FakeVecEnv
+    from tests.helpers import MLP128, ppo_cfg
+    out = []
+    for graph in (False, True):
+        torch.manual_seed(4)
+        env = FakeVecEnv(16, 53, 10, DEV, cloud=False, seed=8)
+        r = ppo(env, ppo_cfg(16, MLP128, device=DEV, cuda_graph=graph, lr=1e-3, lr_schedule=schedule, max_iterations=4), _Logger())
+        curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+        g = torch.Generator().manual_seed(0)
+        lrs = []
+        for it in range(4):
+            eps = torch.randn(8, 16, 10, generator=g).to(DEV)
+            last_obs, last_values = r.collect(curr, None, eps=eps)
+            r.storage.compute_returns(last_values, r.gamma, r.lam)
+            r.update(it + 1)
+            r.storage.clear()
+            curr = r._ingest(last_obs.clone(), r.storage.obs_slot())
+            lrs.append(r.log_dict["Train/learning_rate"])
+            assert abs(float(r.optimizer_actor.opt_state[1]) - lrs[-1]) <= 1e-12 * max(1.0, lrs[-1]) + 1e-9       # the device scalar follows
+            assert abs(float(r.optimizer_critic.opt_state[1]) - 1e-3) < 1e-9
+        want = [max(1e-3 * (1 - (i + 1) / 4), 1e-5) for i in range(4)] if schedule == "linear_decay" else [1e-3, 1e-3, 1e-5, 1e-5]
+        assert lrs == pytest.approx(want, rel=1e-12)
+        out.append({k: v.clone() for k, v in r.actor_critic.state_dict().items()})
+    for k in out[0]:
+        assert torch.equal(out[0][k], out[1][k]), k
