@@ -415,3 +415,41 @@ def test_lr_schedule_reaches_the_replayed_graph(schedule):
         out.append({k: v.clone() for k, v in r.actor_critic.state_dict().items()})
     for k in out[0]:
         assert torch.equal(out[0][k], out[1][k]), k
+
+
+def test_update_with_the_random_sampler_vs_oracle():
+    """`sampler: random` (storage.py:133-137): true gathers instead of slices, a fresh host permutation per epoch — actor epochs first,
+    then the critic's.  One update from a collected buffer against the oracle's update fed by the same generator stream."""
+    from partmanip_b200.algorithms import ppo
+    from partmanip_b200.envs import FakeVecEnv
+    from tests.helpers import MLP128, ppo_cfg
+    E, D, A = 64, 53, 10
+    torch.manual_seed(12)
+    env = FakeVecEnv(E, D, A, DEV, cloud=False, seed=2)
+    cfg = ppo_cfg(E, MLP128, device=DEV, sampler="random", lr=3e-4)
+    r = ppo(env, cfg, _Logger())
+    assert r._graph is None and not r.cuda_graph                           # host-side permutations: no captured update
+    init = {k: v.detach().cpu().clone() for k, v in r.actor_critic.state_dict().items()}
+    curr = r._ingest(env.reset()["obs"], r.storage.obs_slot())
+    last_obs, last_values = r.collect(curr, None)
+    r.storage.compute_returns(last_values, r.gamma, r.lam)
+    st = r.storage
+    flat = lambda t: t.detach().cpu().reshape(-1, t.shape[-1]).clone()
+    buf = dict(obs=flat(st.observations), actions=flat(st.actions), values=flat(st.values), returns=flat(st.returns),
+               logp=flat(st.actions_log_prob), adv=flat(st.advantages), mu=flat(st.mu), sigma=flat(st.sigma))
+    torch.manual_seed(77)                                                  # the permutations come from the default host generator
+    r.update(1)
+    actor = {k[len("actor."):]: v.clone() for k, v in init.items() if k.startswith("actor.")}
+    critic = {k[len("critic."):]: v.clone() for k, v in init.items() if k.startswith("critic.")}
+    log_std = init["log_std"].clone()
+    opt_a, opt_c = O.AdamState({**actor, "log_std": log_std}, 3e-4), O.AdamState(critic, 3e-4)
+    stats = O.ppo_update(actor, critic, log_std, opt_a, opt_c, buf, cfg, "MLP", MLP128, gen=torch.Generator().manual_seed(77))
+    assert stats["count"] == int(r.log_dict["Train/kl_update_count"]) and opt_c.step == r.optimizer_critic.step_count == 40
+    for k, want in (("Train/surrogate_loss", stats["surrogate_loss"]), ("Train/value_function_loss", stats["value_loss"]), ("Train/kl", stats["kl"])):
+        assert abs(float(r.log_dict[k]) - float(want)) <= 1e-3 * max(1.0, abs(float(want))), (k, float(r.log_dict[k]), float(want))
+    got = {k: v.detach().cpu() for k, v in r.actor_critic.state_dict().items()}
+    disp = 40 * 3e-4
+    for k, v in critic.items():
+        assert float((got["critic." + k] - v).abs().max()) <= 0.05 * disp, k
+    for k, v in actor.items():
+        assert float((got["actor." + k] - v).abs().max()) <= 0.05 * disp, k
