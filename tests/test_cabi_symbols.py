@@ -33,6 +33,33 @@ def test_library_exports_every_declared_symbol_and_binding_table_matches():
     assert _lib.lib.pm_adam_ws_bytes(1000) > 0 and _lib.lib.pm_pointnet_head_backward_ws_bytes(2048, 512) > 0
 
 
+def test_binding_table_arity_and_pointer_slots_match_the_header():
+    """Every ctypes signature has exactly the header's parameter count, and pointer / scalar slots line up (a pointer passed in an int slot
+    would be truncated silently)."""
+    import ctypes as C
+    from partmanip_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decls = re.findall(r"\b(?:int|size_t|const char\*)\s+(pm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(decls) >= 60
+    seen = set()
+    for name, params in decls:
+        seen.add(name)
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes), plist)
+        for decl, ct in zip(plist, argtypes):
+            is_ptr_decl = "*" in decl or decl.startswith("pm_stream_t")
+            is_ptr_ct = ct in (C.c_void_p, C.c_char_p) or hasattr(ct, "contents") or (isinstance(ct, type) and issubclass(ct, C._Pointer))
+            assert is_ptr_decl == is_ptr_ct, (name, decl, ct)
+            if not is_ptr_decl:                     # scalar widths: int64_t <-> c_int64, float <-> c_float, ...
+                ctype = decl.rsplit(" ", 1)[0].replace("const ", "").strip()
+                want = {"int": C.c_int, "int32_t": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "float": C.c_float,
+                        "size_t": C.c_size_t, "uint32_t": C.c_uint32}.get(ctype)
+                assert want is not None and ct is want, (name, decl, ct)
+    assert seen == set(_lib.SIGNATURES), sorted(seen ^ set(_lib.SIGNATURES))
+
+
 def test_sm100a_tensor_core_and_no_legacy_mma_in_the_library():
     """The shipped .so carries sm_100a SASS with tcgen05 MMAs (UTCHMMA) and TMEM loads (LDTM) and no legacy HMMA path."""
     from partmanip_b200 import _lib
