@@ -39,11 +39,12 @@ def test_binding_table_arity_and_pointer_slots_match_the_header():
     import ctypes as C
     from partmanip_b200 import _lib
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
-    decls = re.findall(r"\b(?:int|size_t|const char\*)\s+(pm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    decls = re.findall(r"\b(int|size_t|const char\*)\s+(pm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
     assert len(decls) >= 60
     seen = set()
-    for name, params in decls:
+    for ret, name, params in decls:
         seen.add(name)
+        assert _lib.SIGNATURES[name][0] is {"int": C.c_int, "size_t": C.c_size_t, "const char*": C.c_char_p}[ret], (name, ret)
         params = " ".join(params.split())
         plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
         _, argtypes = _lib.SIGNATURES[name]
