@@ -136,7 +136,7 @@ KERNELS_PER_CALL = {
     "pm_accumulate": 1, "pm_dagger_loss": 2, "pm_linear_forward": 1, "pm_linear_backward": 4, "pm_linear_forward_tc": 1, "pm_linear_backward_tc": 5, "pm_pointnet_center": 1,
     "pm_pointnet_encode_forward": 2, "pm_pointnet_encode_backward": 3, "pm_pointnet_head_forward": 1,
     "pm_pointnet_head_backward": 3, "pm_adam_step": 3, "pm_fused_step": 1, "pm_gather_rows": 1,
-    "pm_copy_rows": 1,
+    "pm_copy_rows": 1, "pm_conv3d_first_backward": 2,
 }
 LAUNCHES = [0]
 
