@@ -100,12 +100,12 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu", budget_s=None):
+def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu", budget_s=None, mlp=None):
     """The reference's algorithm (CPU oracle port, unmodified math) for one PPO iteration at E envs; returns
     (env·steps/s, seconds per iteration, timed iterations).  Only bench.py's cpu_baseline / --impl reference / gpu_baseline legs
     call this.  device="cuda:0" runs the same eager-PyTorch restatement on the GPU: the reference's PyTorch-GPU path — fp32,
     TF32 off, eager — the denominator of north_star's ">= 10x" target.  budget_s bounds the timed region (at least one
-    timed iteration always runs)."""
+    timed iteration always runs).  mlp = (obs_dim, hid_dims): the state policy of cfg/algos/ppo.yaml instead of the PointNet encoder."""
     import torch
     from oracle import ppo_oracle as O
     torch.set_num_threads(threads)
@@ -114,12 +114,21 @@ def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu", budget_s=None)
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
     g = torch.Generator().manual_seed(1234)
-    D = N_PTS * CH
-    cfg = ppo_cfg(E, "cpu", "fp32")
-    net = cfg["model"]["network"]
     dv = lambda t: t.to(device)
-    actor = {k: dv(v) for k, v in O.pointnet_init(D, ACT, gen=g).items()}
-    critic = {k: dv(v) for k, v in O.pointnet_init(D, 1, gen=g).items()}
+    if mlp is None:
+        D, kind = N_PTS * CH, "PointNet"
+        cfg = ppo_cfg(E, "cpu", "fp32")
+        net = cfg["model"]["network"]
+        actor = {k: dv(v) for k, v in O.pointnet_init(D, ACT, gen=g).items()}
+        critic = {k: dv(v) for k, v in O.pointnet_init(D, 1, gen=g).items()}
+        fwd = lambda p, x: O.pointnet_forward(p, x)
+    else:
+        D, kind = mlp[0], "MLP"
+        net = dict(name="MLP", hid_dim=list(mlp[1]), activation="tanh")
+        cfg = ppo_cfg(E, "cpu", "fp32", net=net)
+        actor = {k: dv(v) for k, v in O.mlp_init(D, ACT, list(mlp[1]), gen=g).items()}
+        critic = {k: dv(v) for k, v in O.mlp_init(D, 1, list(mlp[1]), gen=g).items()}
+        fwd = lambda p, x: O.mlp_forward(p, x, "tanh")
     log_std = dv(torch.full((ACT,), float(torch.log(torch.tensor(0.5)))))
     opt_a = O.AdamState({**actor, "log_std": log_std}, cfg["lr"])
     opt_c = O.AdamState(critic, cfg["lr"])
@@ -127,6 +136,8 @@ def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu", budget_s=None)
     rs.mean, rs.S, rs.std = dv(rs.mean), dv(rs.S), dv(rs.std)
 
     def obs():
+        if mlp is not None:
+            return dv(torch.randn(E, D, generator=g))
         pc = torch.rand(E, N_PTS, CH, generator=g)
         pc[..., :2] = pc[..., :2] * 2 - 1
         pc[..., 2] = pc[..., 2] * 2 + 0.05
@@ -147,21 +158,21 @@ def cpu_port_iteration(E, threads, iters=1, warm=0, device="cpu", budget_s=None)
         with torch.no_grad():
             cur = rs.normalize(pool[0].clone(), True)
             for t in range(T_STEPS):
-                mu = O.pointnet_forward(actor, cur)
+                mu = fwd(actor, cur)
                 a, lp = O.policy_sample(mu, log_std, rnd(E, ACT), 1.0)
-                v = O.pointnet_forward(critic, cur)
+                v = fwd(critic, cur)
                 for k, x in zip(("obs", "actions", "values", "logp", "mu", "sigma"), (cur, a, v, lp[:, None], mu, log_std.repeat(E, 1))):
                     buf[k].append(x)
                 buf["rew"].append(rnd(E, 1))
                 buf["done"].append(dv(torch.rand(E, 1, generator=g) < 0.05))
                 cur = rs.normalize(pool[t + 1].clone(), True)
-            last = O.pointnet_forward(critic, cur)
+            last = fwd(critic, cur)
             st = {k: torch.stack(v) for k, v in buf.items()}
             ret, adv = O.gae(st["rew"], st["values"], st["done"], torch.zeros_like(st["done"]), last, 0.99, 0.95, None)
         flat = lambda x: x.reshape(-1, x.shape[-1])
         b = dict(obs=flat(st["obs"]), actions=flat(st["actions"]), values=flat(st["values"]), returns=flat(ret),
                  logp=flat(st["logp"]), adv=flat(adv), mu=flat(st["mu"]), sigma=flat(st["sigma"]))
-        O.ppo_update(actor, critic, log_std, opt_a, opt_c, b, cfg, "PointNet", net)
+        O.ppo_update(actor, critic, log_std, opt_a, opt_c, b, cfg, kind, net)
         if on_gpu:
             torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
@@ -618,6 +629,13 @@ def bench_state_mlp(dev, peak_tf, peak_src, kernel_ms):
         ms = e0.elapsed_time(e1) / iters
         out[prec] = {"value": E * T_STEPS / (ms * 1e-3), "unit": "env*steps/s", "ms_per_step": ms, "steps": iters, "warmup": 3}
         r.release_graph()
+    # the same configuration as eager PyTorch on this GPU (the oracle port: fp32, TF32 off) — what the shipped command line runs today
+    try:
+        v, t, n = cpu_port_iteration(E, os.cpu_count() or 1, iters=10, warm=3, device=dev, budget_s=20, mlp=(D, (512, 512, 512)))
+        out["gpu_baseline"] = {"value": v, "unit": "env*steps/s", "ms_per_step": t * 1e3, "steps": n, "warmup": 3, "dtype": "f32", "kind": "port",
+                               "speedup_fp32_mode": out["fp32"]["value"] / v, "speedup_bf16_mode": out["bf16"]["value"] / v}
+    except Exception as e:  # pragma: no cover
+        out["gpu_baseline"] = {"error": repr(e)[:200]}
     # dominant GEMM: one 512 x 512 fc layer over a 2048-row minibatch (forward), rotating over 8 input buffers
     M, N, K = 2048, 512, 512
     xs = [torch.randn(M, K, device=dev) for _ in range(8)]
