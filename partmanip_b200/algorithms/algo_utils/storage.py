@@ -6,6 +6,10 @@ device index tensors consumed by pm_gather_rows.
 """
 from __future__ import annotations
 
+import os
+from os.path import join as pjoin
+
+import numpy as np
 import torch
 
 from ... import ops
@@ -89,6 +93,44 @@ class RolloutStorage:
         self.mix_buf_ind = (self.mix_buf_ind + self.num_envs) % max_buf_size
         if self.cur_buf_size < max_buf_size:
             self.cur_buf_size += self.num_envs
+
+    def add_transitions_offline(self, folder, device, add_proprio_obs=False, chunk=256):
+        """storage.py:58-82: pre-fill the DAgger ring from recorded steps, <folder>/<scene>/<step>.npy (sorted), each a pickled dict
+        (tsdf, proprio_state, tea_obs), one ring row per file, wrapping like the online path.  The reference copies row by row; here
+        the rows are staged on the host and moved `chunk` at a time."""
+        print('Read offline data from ', folder)
+        scene_list = sorted(os.listdir(folder))
+        step_list = sorted(os.listdir(pjoin(folder, scene_list[0])))
+        max_buf_size = self.n_steps * self.num_envs
+        stu_rows, tea_rows = [], []
+
+        def flush():
+            k = len(stu_rows)
+            if not k:
+                return
+            stu = torch.from_numpy(np.stack(stu_rows)).to(device)
+            tea = torch.from_numpy(np.stack(tea_rows)).to(device)
+            done = 0
+            while done < k:                                              # split where the ring wraps
+                n = min(k - done, max_buf_size - self.mix_buf_ind)
+                ops.copy_rows(stu[done:done + n], self.observations[self.mix_buf_ind:self.mix_buf_ind + n])
+                ops.copy_rows(tea[done:done + n], self.tea_obs[self.mix_buf_ind:self.mix_buf_ind + n])
+                self.mix_buf_ind = (self.mix_buf_ind + n) % max_buf_size
+                self.cur_buf_size = min(self.cur_buf_size + n, max_buf_size)
+                self.rows_added += n
+                done += n
+            self.last_episode_buf_ind = self.mix_buf_ind
+            stu_rows.clear()
+            tea_rows.clear()
+        for scene in scene_list:
+            for step in step_list:
+                data = np.load(pjoin(folder, scene, step), allow_pickle=True).item()
+                tsdf = np.asarray(data['tsdf'], dtype=np.float32).reshape(-1)
+                stu_rows.append(np.concatenate((tsdf, np.asarray(data['proprio_state'], dtype=np.float32).reshape(-1))) if add_proprio_obs else tsdf)
+                tea_rows.append(np.asarray(data['tea_obs'], dtype=np.float32).reshape(-1))
+                if len(stu_rows) == chunk:
+                    flush()
+        flush()
 
     def clear(self):
         self.step = 0

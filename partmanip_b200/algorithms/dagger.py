@@ -3,7 +3,7 @@ state teacher labels, a ring buffer (storage.py:20-27, 84-91) feeds an MSE updat
 
 Same constructor `(vec_env, cfg, logger)`, cfg keys, checkpoint keys and log keys.  The student forward/backward,
 the teacher forward, the loss and the Adam step run in libpartmanip_b200.so; minibatches of the random sampler are
-gathered with pm_gather_rows.  Differences, on purpose: `teacher_reward.npy` is only required when
+gathered with pm_gather_rows; `offline_data_pth` prefills the ring from recorded steps (storage.py:58-82).  Differences, on purpose: `teacher_reward.npy` is only required when
 `reward_reset` is on (the reference loads it unconditionally, dagger.py:33); the per-step debug prints are dropped.
 """
 from __future__ import annotations
@@ -43,8 +43,6 @@ class dagger:
         self.vec_env, self.logger = vec_env, logger
         for attr, key in _CFG_ATTRS:
             setattr(self, attr, cfg[key])
-        if self.offline_data_pth is not None:
-            raise NotImplementedError("offline TSDF replay (storage.add_transitions_offline) is outside the hot path")
         if self.reward_reset:
             self.tea_rew = torch.tensor(np.load('teacher_reward.npy')).to(self.device)
         self.stu_num_obs = self.stu_input_obs = vec_env.num_obs[self.stu_obs_mode]
@@ -180,6 +178,8 @@ class dagger:
             self.eval()
             self.logger.info(self.log_dict, self.curr_iter)
             return
+        if self.offline_data_pth is not None:                        # dagger.py:186-187: recorded steps first
+            self.storage.add_transitions_offline(self.offline_data_pth, self.device, self.add_proprio_obs)
         stu_obs, tea_obs = self._reset_env()
         while self.curr_iter < self.max_iter:
             self.curr_iter += 1

@@ -1,13 +1,14 @@
 """Synthetic offline TSDF dataset in the layout algorithms/bc.py:12-31 reads: <root>/scene_xxxxx/step_yyyyy.npy, each a pickled
-dict(tsdf (R, R, R) float32, action (A,), proprio_state (1, P)).  Deterministic in `seed`; shared by the golden generator and the
+dict(tsdf (R, R, R) float32, action (A,), proprio_state (1, P), tea_obs (T,)).  Deterministic in `seed`; shared by the golden generator and the
 GPU test (a 50^3 volume is 500 KB: the files are generated, not committed)."""
 import os
 
 import numpy as np
 
 
-def write_dataset(root, seed=0, scenes=3, steps=4, R=50, A=10, P=31):
+def write_dataset(root, seed=0, scenes=3, steps=4, R=50, A=10, P=31, T=53):
     rng = np.random.default_rng(seed)
+    rng_tea = np.random.default_rng(seed + 1000003)        # separate stream: the volumes / actions / states above stay what the goldens saw
     zz, yy, xx = np.meshgrid(*[np.linspace(-1, 1, R, dtype=np.float32)] * 3, indexing="ij")
     for s in range(scenes):
         d = os.path.join(root, f"scene_{s:05d}")
@@ -19,7 +20,8 @@ def write_dataset(root, seed=0, scenes=3, steps=4, R=50, A=10, P=31):
             tsdf += rng.normal(0, 0.02, size=tsdf.shape).astype(np.float32)
             action = np.tanh(rng.normal(0, 1, size=A)).astype(np.float32)
             state = rng.normal(0, 1, size=(1, P)).astype(np.float32)
-            np.save(os.path.join(d, f"step_{t:05d}.npy"), dict(tsdf=tsdf, action=action, proprio_state=state), allow_pickle=True)
+            tea = rng_tea.normal(0, 1, size=T).astype(np.float32)          # storage.py:75 `tea_obs` (DAgger's offline prefill; bc ignores it)
+            np.save(os.path.join(d, f"step_{t:05d}.npy"), dict(tsdf=tsdf, action=action, proprio_state=state, tea_obs=tea), allow_pickle=True)
     return scenes * steps
 
 

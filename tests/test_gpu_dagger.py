@@ -123,3 +123,32 @@ def test_cached_teacher_labels_are_bit_identical_to_recomputing(tmp_path):
     for k in runs[0][1]:
         assert torch.equal(runs[0][1][k], runs[1][1][k]), k
     assert any(not torch.equal(runs[0][1][k], runs[0][0][k]) for k in runs[0][1] if k.startswith("actor."))
+
+
+def test_offline_prefill_of_the_ring(tmp_path):
+    """storage.py:58-82 add_transitions_offline: recorded (tsdf [+ proprio], tea_obs) steps enter the ring in sorted scene / step order, one
+    row per file, wrapping like the online path; the DAgger runner prefills before its first rollout (dagger.py:186-187)."""
+    import os
+    import numpy as np
+    from partmanip_b200.algorithms.algo_utils import RolloutStorage
+    from tests.helpers_bc import write_dataset
+    R, P, T = 6, 5, 7
+    n = write_dataset(str(tmp_path / "data"), seed=2, scenes=3, steps=4, R=R, A=10, P=P, T=T)        # 12 rows
+    rows = []
+    for sc in sorted(os.listdir(str(tmp_path / "data"))):
+        for stp in sorted(os.listdir(str(tmp_path / "data" / sc))):
+            d = np.load(str(tmp_path / "data" / sc / stp), allow_pickle=True).item()
+            rows.append((np.concatenate((d["tsdf"].reshape(-1), d["proprio_state"].reshape(-1))), d["tea_obs"]))
+    want_stu = torch.from_numpy(np.stack([r[0] for r in rows]))
+    want_tea = torch.from_numpy(np.stack([r[1] for r in rows]))
+    for cap_steps, chunk in ((8, 5), (2, 256), (2, 3)):                                  # capacity 4 * steps rows: 32 (no wrap) or 8 (wraps)
+        st = RolloutStorage(4, cap_steps, R ** 3 + P, 10, DEV, sampler="random", tea_obs_shape=T, max_length=10)
+        st.add_transitions_offline(str(tmp_path / "data"), DEV, add_proprio_obs=True, chunk=chunk)
+        cap = 4 * cap_steps
+        assert st.cur_buf_size == min(n, cap) and st.mix_buf_ind == n % cap and st.last_episode_buf_ind == st.mix_buf_ind and st.rows_added == n
+        for i in range(n):                                                                # the last write to a slot wins
+            if i >= n - cap:
+                assert torch.equal(st.observations[i % cap].cpu(), want_stu[i]) and torch.equal(st.tea_obs[i % cap].cpu(), want_tea[i]), (cap, i)
+    st = RolloutStorage(4, 8, R ** 3, 10, DEV, sampler="random", tea_obs_shape=T, max_length=10)
+    st.add_transitions_offline(str(tmp_path / "data"), DEV, add_proprio_obs=False)
+    assert torch.equal(st.observations[:n].cpu(), want_stu[:, :R ** 3])

@@ -79,6 +79,7 @@ def _runner(monkeypatch, **over):
     r.n_steps, r.max_iter, r.curr_iter, r.eval_freq, r.save_freq, r.eval_round = 3, 4, 0, 2, 100, 2
     r.max_episode_length, r.test_only, r.save_video, r.save_pose, r.reward_reset = 5, False, False, False, False
     r.cache_teacher_actions = False
+    r.offline_data_pth = None
     r.total_envsteps = r.total_time = 0
     r.update = lambda it: r.log_dict.update({'Train/learning_rate': 0.1, 'Train/dagger_loss': 1.0 / it})
     for k, v in over.items():
