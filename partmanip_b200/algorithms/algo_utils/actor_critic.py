@@ -31,7 +31,8 @@ class ActorCritic(nn.Module):
         cls = _NETWORKS[net_cfg['name']]
         self.actor = cls(obs_shape, actions_shape, net_cfg, proprio_shape=proprio_shape)     # policy
         self.critic = cls(obs_shape, 1, net_cfg, proprio_shape=proprio_shape)                # value function
-        self.log_std = nn.Parameter(np.log(model_cfg['action_std']) * torch.ones(actions_shape))
+        with np.errstate(divide='ignore'):      # bc.yaml ships action_std 0.0: log_std = -inf, exactly as in the reference (actor_critic.py:21)
+            self.log_std = nn.Parameter(np.log(model_cfg['action_std']) * torch.ones(actions_shape))
         self.max_action = model_cfg['clipAction']
         assert self.max_action > 0
         self.action_activate = model_cfg['action_activate']
