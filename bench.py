@@ -588,10 +588,67 @@ def bench_dagger(dev, precision):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    return {"value": E / (ms * 1e-3), "unit": "env*steps/s", "ms_per_step": ms, "steps": iters, "warmup": 2, "dtype": precision,
-            "workload": f"dagger: {E} envs x {NP}-pt clouds, buffer 16 x {E} rows, random sampler, 2 epochs x 16 minibatches of 2048, "
-                        "teacher MLP 53->512^3->10; one step = 1 env step for all envs + update",
-            "dagger_loss": float(r.log_dict["Train/dagger_loss"])}
+    out = {"value": E / (ms * 1e-3), "unit": "env*steps/s", "ms_per_step": ms, "steps": iters, "warmup": 2, "dtype": precision,
+           "workload": f"dagger: {E} envs x {NP}-pt clouds, buffer 16 x {E} rows, random sampler, 2 epochs x 16 minibatches of 2048, "
+                       "teacher MLP 53->512^3->10; one step = 1 env step for all envs + update",
+           "dagger_loss": float(r.log_dict["Train/dagger_loss"])}
+    del r, env, stu, tea
+    torch.cuda.empty_cache()
+    try:                                                  # the same step as eager PyTorch on this GPU (oracle port; one warm + one timed step)
+        v, t, n = torch_dagger_step(dev, E=E, NP=NP, iters=1, warm=1)
+        out["gpu_baseline"] = {"value": v, "unit": "env*steps/s", "ms_per_step": t * 1e3, "steps": n, "warmup": 1, "dtype": "f32", "kind": "port",
+                               "speedup": out["value"] / v}
+    except Exception as e:  # pragma: no cover
+        out["gpu_baseline"] = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def torch_dagger_step(device, E=2048, NP=2048, iters=1, warm=1, mb=2048, n_mb=16, epochs=2, buf_steps=16, hid=(512, 512, 512)):
+    """BASELINE config 4 as eager PyTorch (the oracle port of dagger.py:205-337, fp32, TF32 off) on `device`: one step = the student's
+    exploration forward on E clouds, the ring append, and n_updates x n_minibatches update steps, each with its own teacher forward
+    (dagger.py:311) and a gathered minibatch.  Returns (env·steps/s, seconds per step, timed steps).  Only the DAgger config's
+    gpu_baseline calls this."""
+    import torch
+    from oracle import ppo_oracle as O
+    on_gpu = str(device).startswith("cuda")
+    if on_gpu:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    A, Dt, D = 10, 53, NP * CH
+    g = torch.Generator().manual_seed(21)
+    dv = lambda t: t.to(device)
+    student = {k: dv(v) for k, v in O.pointnet_init(D, A, point_num=NP, gen=g).items()}
+    teacher = {k: dv(v) for k, v in O.mlp_init(Dt, A, list(hid), gen=g).items()}
+    log_std = dv(torch.full((A,), -2.3))
+    opt = O.AdamState(student, 5e-5)
+    net = dict(name="PointNet", activation="tanh", max_mean=False, sub_mean=False, point_num=NP)
+    rows = buf_steps * E
+    ring_s, ring_t = dv(torch.rand(rows, D, generator=g) * 2 - 1), dv(torch.randn(rows, Dt, generator=g))
+    obs, tea_obs = dv(torch.rand(E, D, generator=g) * 2 - 1), dv(torch.randn(E, Dt, generator=g))
+    times, slot = [], 0
+    for it in range(warm + iters):
+        if on_gpu:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            mu = O.pointnet_forward(student, obs.clone(), point_num=NP)
+            O.policy_sample(mu, log_std, dv(torch.randn(E, A, generator=g)), 1.0)
+            ring_s[slot:slot + E].copy_(obs)
+            ring_t[slot:slot + E].copy_(tea_obs)
+            slot = (slot + E) % rows
+        for _ in range(epochs):
+            perm = torch.randperm(rows, generator=g)
+            for k in range(n_mb):
+                idx = dv(perm[k * mb:(k + 1) * mb])
+                with torch.no_grad():
+                    tea_act = O.action_activation(O.mlp_forward(teacher, ring_t[idx], "tanh"), 1.0)
+                O.dagger_update_step(opt.params, opt, ring_s[idx], tea_act, "PointNet", net, 1.0)
+        if on_gpu:
+            torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warm:]) / max(len(times[warm:]), 1)
+    return E / t, t, len(times[warm:])
 
 
 def bench_state_mlp(dev, peak_tf, peak_src, kernel_ms):
